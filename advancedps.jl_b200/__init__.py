@@ -1,0 +1,11 @@
+"""B200-native SMC / particle-MCMC inner loop behind the AdvancedPS.jl sampler surface.
+
+Layout: ``csrc/`` holds the sm_100a CUDA kernels and the C-ABI shim (``libaps_b200.so``,
+declared in ``include/aps_b200.h``); the Python modules are the host-side mirror of the
+reference's sampler interface (src/smc.jl, src/container.jl, src/resampling.jl) over that ABI.
+"""
+from . import _abi, models  # noqa: F401
+from ._abi import (  # noqa: F401
+    RESAMPLE_MULTINOMIAL, RESAMPLE_RESIDUAL, RESAMPLE_STRATIFIED, RESAMPLE_SYSTEMATIC,
+    SAMPLER_PG, SAMPLER_PGAS, SAMPLER_SMC,
+)

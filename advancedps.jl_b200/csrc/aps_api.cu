@@ -1,0 +1,732 @@
+// aps_api.cu -- C ABI of libaps_b200.so (include/aps_b200.h): handle lifetime, sweep
+// orchestration (CUDA graph of the per-step kernels), result accessors, operator-level entry
+// points and the resample-kernel micro-benchmark. No torch types; plain pointers and sizes.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+#include <math.h>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "aps_kernels.cuh"
+
+// ------------------------------------------------------------------ errors
+static thread_local std::string g_err;
+
+static int fail(int code, const std::string &msg) {
+    g_err = msg;
+    return code;
+}
+#define CU(call)                                                                                       \
+    do {                                                                                               \
+        cudaError_t e_ = (call);                                                                       \
+        if (e_ != cudaSuccess)                                                                         \
+            return fail(e_ == cudaErrorMemoryAllocation ? APS_ERR_NOMEM : APS_ERR_CUDA,                \
+                        std::string(#call) + ": " + cudaGetErrorString(e_));                           \
+    } while (0)
+
+extern "C" const char *aps_last_error(void) { return g_err.c_str(); }
+extern "C" const char *aps_version(void) { return "aps_b200 0.1 (sm_100a)"; }
+
+// ------------------------------------------------------------------ kernel dispatch tables
+typedef void (*prop_fn)(const DevCtx, const long long);
+typedef void (*step_fn)(const DevCtx, const long long);
+
+template <int OBS>
+static prop_fn prop_for_dim(int d) {
+    switch (d) {
+        case 1: return k_propagate<1, OBS>;
+        case 2: return k_propagate<2, OBS>;
+        case 3: return k_propagate<3, OBS>;
+        default: return k_propagate<4, OBS>;
+    }
+}
+static prop_fn pick_propagate(int obs, int d) {
+    switch (obs) {
+        case APS_OBS_LINEAR_GAUSS: return prop_for_dim<APS_OBS_LINEAR_GAUSS>(d);
+        case APS_OBS_STOCH_VOL: return prop_for_dim<APS_OBS_STOCH_VOL>(d);
+        default: return prop_for_dim<APS_OBS_CONST>(d);
+    }
+}
+static step_fn pick_pgas_max(int d) {
+    switch (d) {
+        case 1: return k_pgas_max<1>;
+        case 2: return k_pgas_max<2>;
+        case 3: return k_pgas_max<3>;
+        default: return k_pgas_max<4>;
+    }
+}
+static step_fn pick_pgas_select(int d) {
+    switch (d) {
+        case 1: return k_pgas_select<1>;
+        case 2: return k_pgas_select<2>;
+        case 3: return k_pgas_select<3>;
+        default: return k_pgas_select<4>;
+    }
+}
+static step_fn pick_resample(int kind) {
+    switch (kind) {
+        case APS_RESAMPLE_STRATIFIED: return k_resample<APS_RESAMPLE_STRATIFIED>;
+        default: return k_resample<APS_RESAMPLE_SYSTEMATIC>;
+    }
+}
+
+static int g_sm_count = 0;
+static int sm_count() {
+    if (g_sm_count == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
+        if (g_sm_count <= 0) g_sm_count = 148;
+    }
+    return g_sm_count;
+}
+// grid for the grid-stride kernels: a multiple of the SM count, 8 resident CTAs of 256 per SM
+static int stride_grid(long long n) {
+    long long need = (n + APS_THREADS - 1) / APS_THREADS;
+    long long cap = (long long)sm_count() * 8;
+    if (need < 1) need = 1;
+    return (int)(need < cap ? need : cap);
+}
+
+// ------------------------------------------------------------------ handle
+struct aps_handle {
+    aps_config cfg;
+    DevCtx ctx;
+    cudaStream_t stream;
+    cudaEvent_t ev0, ev1;
+    SweepParams *d_sp;
+    double *d_ref, *d_traj, *d_Y, *d_scratch;  // d_scratch: N x d doubles for accessors
+    SweepParams *h_sp;                          // pinned
+    SweepState *h_st;                           // pinned
+    cudaGraphExec_t graph;
+    bool graph_ready, has_obs, swept, ref_valid;
+    float last_ms;
+    long long last_launches, graph_nodes;
+    prop_fn f_prop;
+    step_fn f_res, f_pmax, f_psel;
+};
+
+static void free_handle(aps_handle *h) {
+    if (!h) return;
+    cudaSetDevice(h->cfg.device);
+    if (h->graph_ready) cudaGraphExecDestroy(h->graph);
+    cudaFree(h->ctx.x);
+    cudaFree(h->ctx.anc);
+    cudaFree(h->ctx.logw);
+    cudaFree(h->ctx.q);
+    cudaFree(h->ctx.tile_sum);
+    cudaFree(h->ctx.tile_s1);
+    cudaFree(h->ctx.tile_s2);
+    cudaFree(h->ctx.tile_prefix);
+    cudaFree(h->ctx.acc);
+    cudaFree(h->ctx.plan);
+    cudaFree(h->ctx.st);
+    cudaFree(h->d_sp);
+    cudaFree(h->d_ref);
+    cudaFree(h->d_traj);
+    cudaFree(h->d_Y);
+    cudaFree(h->d_scratch);
+    if (h->h_sp) cudaFreeHost(h->h_sp);
+    if (h->h_st) cudaFreeHost(h->h_st);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+extern "C" int aps_create(const aps_config *cfg, aps_handle **out) {
+    if (!cfg || !out) return fail(APS_ERR_INVALID, "aps_create: null argument");
+    *out = nullptr;
+    const long long N = cfg->n_particles, T = cfg->n_steps;
+    if (N < 1 || N > 2147483647LL) return fail(APS_ERR_INVALID, "aps_create: n_particles must be in 1..2^31-1");
+    if (T < 1) return fail(APS_ERR_INVALID, "aps_create: n_steps must be >= 1");
+    if (cfg->sampler < APS_SMC || cfg->sampler > APS_PGAS) return fail(APS_ERR_INVALID, "aps_create: unknown sampler");
+    if (cfg->resampler < APS_RESAMPLE_MULTINOMIAL || cfg->resampler > APS_RESAMPLE_SYSTEMATIC)
+        return fail(APS_ERR_INVALID, "aps_create: unknown resampler");
+    if (cfg->resampler == APS_RESAMPLE_MULTINOMIAL || cfg->resampler == APS_RESAMPLE_RESIDUAL)
+        return fail(APS_ERR_INVALID, "aps_create: multinomial / residual resampling inside the sweep is not built yet");
+    if (cfg->sampler != APS_SMC && !cfg->keep_history)
+        return fail(APS_ERR_INVALID, "aps_create: PG / PGAS need keep_history = 1 (trajectory extraction)");
+    if (cfg->world_size != 1 || cfg->rank != 0)
+        return fail(APS_ERR_INVALID, "aps_create: multi-GPU sharding is not built yet (world_size must be 1)");
+    aps_handle *h = new aps_handle();
+    memset(h, 0, sizeof(*h));
+    h->cfg = *cfg;
+    if (aps_model_prepare(&cfg->model, &h->ctx.md)) {
+        delete h;
+        return fail(APS_ERR_INVALID, "aps_create: invalid model (dimensions 1..4, positive noise scales)");
+    }
+#define CUH(call)                                                          \
+    do {                                                                   \
+        cudaError_t e_ = (call);                                           \
+        if (e_ != cudaSuccess) {                                           \
+            free_handle(h);                                                \
+            return fail(e_ == cudaErrorMemoryAllocation ? APS_ERR_NOMEM : APS_ERR_CUDA, \
+                        std::string(#call) + ": " + cudaGetErrorString(e_)); \
+        }                                                                  \
+    } while (0)
+    CUH(cudaSetDevice(cfg->device));
+    CUH(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    CUH(cudaEventCreate(&h->ev0));
+    CUH(cudaEventCreate(&h->ev1));
+    DevCtx &c = h->ctx;
+    const int d = cfg->model.d;
+    c.N = N;
+    c.T = T;
+    c.d = d;
+    c.dy = cfg->model.dy;
+    c.S = aps_weight_shift((uint64_t)N);
+    c.Hs = aps_ess_shift((uint64_t)N);
+    c.sampler = cfg->sampler;
+    c.resampler = cfg->resampler;
+    c.bare = (cfg->ess_threshold != cfg->ess_threshold) ? 1 : 0;
+    c.ess_threshold = cfg->ess_threshold;
+    c.logN = aps_log((double)N);
+    c.n_override = 0;
+    c.x_slabs = cfg->keep_history ? T : 2;
+    c.anc_slabs = cfg->keep_history ? T + 1 : 2;
+    c.num_tiles = (N + APS_TILE - 1) / APS_TILE;
+    CUH(cudaMalloc(&c.x, sizeof(double) * (size_t)c.x_slabs * d * N));
+    CUH(cudaMalloc(&c.anc, sizeof(int32_t) * (size_t)c.anc_slabs * N));
+    CUH(cudaMalloc(&c.logw, sizeof(double) * (size_t)N));
+    CUH(cudaMalloc(&c.q, sizeof(u64) * (size_t)N));
+    CUH(cudaMalloc(&c.tile_sum, sizeof(u64) * (size_t)c.num_tiles));
+    CUH(cudaMalloc(&c.tile_s1, sizeof(u64) * (size_t)c.num_tiles));
+    CUH(cudaMalloc(&c.tile_s2, sizeof(u64) * (size_t)c.num_tiles));
+    CUH(cudaMalloc(&c.tile_prefix, sizeof(u64) * (size_t)c.num_tiles));
+    CUH(cudaMalloc(&c.acc, sizeof(StepAcc) * (size_t)(T + 2)));
+    CUH(cudaMalloc(&c.plan, sizeof(StepPlan) * (size_t)(T + 2)));
+    CUH(cudaMalloc(&c.st, sizeof(SweepState)));
+    CUH(cudaMalloc(&h->d_sp, sizeof(SweepParams)));
+    CUH(cudaMalloc(&h->d_ref, sizeof(double) * (size_t)T * d));
+    CUH(cudaMalloc(&h->d_traj, sizeof(double) * (size_t)T * d));
+    CUH(cudaMalloc(&h->d_Y, sizeof(double) * (size_t)T * c.dy));
+    CUH(cudaMalloc(&h->d_scratch, sizeof(double) * (size_t)N * d));
+    CUH(cudaMallocHost(&h->h_sp, sizeof(SweepParams)));
+    CUH(cudaMallocHost(&h->h_st, sizeof(SweepState)));
+    CUH(cudaMemset(c.plan, 0, sizeof(StepPlan) * (size_t)(T + 2)));
+    c.Y = h->d_Y;
+    c.ref = h->d_ref;
+    c.sp = h->d_sp;
+    h->f_prop = pick_propagate(cfg->model.obs_kind, d);
+    h->f_res = pick_resample(cfg->resampler);
+    h->f_pmax = pick_pgas_max(d);
+    h->f_psel = pick_pgas_select(d);
+#undef CUH
+    *out = h;
+    return APS_OK;
+}
+
+extern "C" int aps_destroy(aps_handle *h) {
+    free_handle(h);
+    return APS_OK;
+}
+
+extern "C" int aps_set_observations(aps_handle *h, const double *Y, int64_t T, int64_t dy) {
+    if (!h || !Y) return fail(APS_ERR_INVALID, "aps_set_observations: null argument");
+    if (T != h->cfg.n_steps || dy != h->cfg.model.dy)
+        return fail(APS_ERR_INVALID, "aps_set_observations: shape does not match the handle (T x dy)");
+    CU(cudaSetDevice(h->cfg.device));
+    CU(cudaMemcpyAsync(h->d_Y, Y, sizeof(double) * (size_t)T * dy, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    h->has_obs = true;
+    return APS_OK;
+}
+
+// enqueue every kernel of one sweep on the handle's stream; returns the number of launches
+static long long enqueue_sweep(aps_handle *h) {
+    const DevCtx &c = h->ctx;
+    cudaStream_t st = h->stream;
+    long long n = 0;
+    cudaMemsetAsync(c.acc, 0, sizeof(StepAcc) * (size_t)(c.T + 2), st);
+    k_init_sweep<<<1, 32, 0, st>>>(c);
+    ++n;
+    const int gp = stride_grid(c.N);
+    const int gt = (int)c.num_tiles;
+    for (long long t = 1; t <= c.T; ++t) {
+        h->f_prop<<<gp, APS_THREADS, 0, st>>>(c, t);
+        k_normalise<IN_LOGW><<<gt, APS_THREADS, 0, st>>>(c, c.logw, t);
+        h->f_res<<<gt, APS_THREADS, 0, st>>>(c, t);
+        n += 3;
+        if (c.sampler == APS_PGAS && t >= 2 && t <= c.T - 1) {
+            h->f_pmax<<<gp, APS_THREADS, 0, st>>>(c, t);
+            h->f_psel<<<gt, APS_THREADS, 0, st>>>(c, t);
+            n += 2;
+        }
+    }
+    return n;
+}
+
+extern "C" int aps_sweep(aps_handle *h, uint64_t master_seed, const double *ref_traj, double *logevidence) {
+    if (!h || !logevidence) return fail(APS_ERR_INVALID, "aps_sweep: null argument");
+    if (!h->has_obs) return fail(APS_ERR_INVALID, "aps_sweep: observations not set");
+    CU(cudaSetDevice(h->cfg.device));
+    const DevCtx &c = h->ctx;
+    int has_ref = 0;
+    if (ref_traj != nullptr) {
+        if (h->cfg.sampler == APS_SMC) return fail(APS_ERR_INVALID, "aps_sweep: SMC takes no reference trajectory");
+        if (c.N < 2) return fail(APS_ERR_INVALID, "aps_sweep: a conditional sweep needs at least 2 particles");
+        if (ref_traj == APS_REF_ON_DEVICE) {
+            if (!h->ref_valid) return fail(APS_ERR_INVALID, "aps_sweep: no trajectory has been picked yet");
+        } else {
+            CU(cudaMemcpyAsync(h->d_ref, ref_traj, sizeof(double) * (size_t)c.T * c.d, cudaMemcpyHostToDevice, h->stream));
+            h->ref_valid = true;
+        }
+        has_ref = 1;
+    }
+    h->h_sp->key = master_seed;
+    h->h_sp->has_ref = has_ref;
+    h->h_sp->pad = 0;
+    CU(cudaMemcpyAsync(h->d_sp, h->h_sp, sizeof(SweepParams), cudaMemcpyHostToDevice, h->stream));
+    if (!h->graph_ready) {
+        cudaGraph_t g;
+        CU(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+        h->graph_nodes = enqueue_sweep(h);
+        CU(cudaStreamEndCapture(h->stream, &g));
+        CU(cudaGraphInstantiate(&h->graph, g, 0));
+        CU(cudaGraphDestroy(g));
+        h->graph_ready = true;
+    }
+    CU(cudaEventRecord(h->ev0, h->stream));
+    CU(cudaGraphLaunch(h->graph, h->stream));
+    CU(cudaEventRecord(h->ev1, h->stream));
+    CU(cudaMemcpyAsync(h->h_st, c.st, sizeof(SweepState), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaGetLastError());
+    CU(cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1));
+    h->last_launches = h->graph_nodes;
+    h->swept = true;
+    if (h->h_st->err)
+        return fail(h->h_st->err, "aps_sweep: particle weights could not be normalised (all -Inf or NaN log-weights)");
+    *logevidence = h->h_st->logev;
+    return APS_OK;
+}
+
+#define NEED_SWEEP(name)                                                        \
+    if (!h) return fail(APS_ERR_INVALID, name ": null handle");                 \
+    if (!h->swept) return fail(APS_ERR_INVALID, name ": no sweep has run yet"); \
+    CU(cudaSetDevice(h->cfg.device));
+
+extern "C" int aps_pick_trajectory(aps_handle *h, double *traj_out, int64_t *index_out) {
+    NEED_SWEEP("aps_pick_trajectory");
+    if (!h->cfg.keep_history) return fail(APS_ERR_INVALID, "aps_pick_trajectory: handle was created with keep_history = 0");
+    const DevCtx &c = h->ctx;
+    k_pick<<<1, APS_THREADS, 0, h->stream>>>(c, c.T, c.T + 1, APS_DOM_PICK);
+    k_backtrace<<<1, 32, 0, h->stream>>>(c, -1, h->d_traj);
+    CU(cudaMemcpyAsync(h->d_ref, h->d_traj, sizeof(double) * (size_t)c.T * c.d, cudaMemcpyDeviceToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->h_st, c.st, sizeof(SweepState), cudaMemcpyDeviceToHost, h->stream));
+    if (traj_out)
+        CU(cudaMemcpyAsync(traj_out, h->d_traj, sizeof(double) * (size_t)c.T * c.d, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaGetLastError());
+    if (h->h_st->picked_slot < 0) return fail(APS_ERR_WEIGHTS, "aps_pick_trajectory: no particle could be selected");
+    h->ref_valid = true;
+    if (index_out) *index_out = h->h_st->picked_slot;
+    return APS_OK;
+}
+
+static int final_resampled(aps_handle *h, int *out) {
+    StepPlan p;
+    CU(cudaMemcpyAsync(&p, h->ctx.plan + h->ctx.T, sizeof(StepPlan), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    *out = p.resampled;
+    return APS_OK;
+}
+
+extern "C" int aps_get_weights(aps_handle *h, double *w_out) {
+    NEED_SWEEP("aps_get_weights");
+    if (!w_out) return fail(APS_ERR_INVALID, "aps_get_weights: null output");
+    const DevCtx &c = h->ctx;
+    k_weights_out<<<stride_grid(c.N), APS_THREADS, 0, h->stream>>>(c.q, c.plan + c.T, c.N, c.S, 1, h->d_scratch);
+    CU(cudaMemcpyAsync(w_out, h->d_scratch, sizeof(double) * (size_t)c.N, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaGetLastError());
+    return APS_OK;
+}
+
+extern "C" int aps_get_logweights(aps_handle *h, double *logw_out) {
+    NEED_SWEEP("aps_get_logweights");
+    if (!logw_out) return fail(APS_ERR_INVALID, "aps_get_logweights: null output");
+    int res = 0;
+    int rc = final_resampled(h, &res);
+    if (rc) return rc;
+    if (res) {  // reset_logweights! after the final resampling (src/container.jl:228)
+        memset(logw_out, 0, sizeof(double) * (size_t)h->ctx.N);
+        return APS_OK;
+    }
+    CU(cudaMemcpyAsync(logw_out, h->ctx.logw, sizeof(double) * (size_t)h->ctx.N, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return APS_OK;
+}
+
+extern "C" int aps_get_final_states(aps_handle *h, double *x_out) {
+    NEED_SWEEP("aps_get_final_states");
+    if (!x_out) return fail(APS_ERR_INVALID, "aps_get_final_states: null output");
+    const DevCtx &c = h->ctx;
+    k_gather_final<<<stride_grid(c.N), APS_THREADS, 0, h->stream>>>(c, h->d_scratch);
+    CU(cudaMemcpyAsync(x_out, h->d_scratch, sizeof(double) * (size_t)c.N * c.d, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaGetLastError());
+    return APS_OK;
+}
+
+extern "C" int aps_get_trajectory(aps_handle *h, int64_t slot, double *traj_out) {
+    NEED_SWEEP("aps_get_trajectory");
+    if (!traj_out) return fail(APS_ERR_INVALID, "aps_get_trajectory: null output");
+    if (!h->cfg.keep_history) return fail(APS_ERR_INVALID, "aps_get_trajectory: handle was created with keep_history = 0");
+    const DevCtx &c = h->ctx;
+    if (slot < 0 || slot >= c.N) return fail(APS_ERR_INVALID, "aps_get_trajectory: slot out of range");
+    k_backtrace<<<1, 32, 0, h->stream>>>(c, slot, h->d_traj);
+    CU(cudaMemcpyAsync(traj_out, h->d_traj, sizeof(double) * (size_t)c.T * c.d, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaGetLastError());
+    return APS_OK;
+}
+
+extern "C" int aps_get_step_stats(aps_handle *h, double *logz_out, double *ess_out, uint8_t *resampled_out) {
+    NEED_SWEEP("aps_get_step_stats");
+    const long long T = h->ctx.T;
+    std::vector<StepPlan> p((size_t)T + 1);
+    CU(cudaMemcpyAsync(p.data(), h->ctx.plan, sizeof(StepPlan) * (size_t)(T + 1), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    for (long long s = 0; s <= T; ++s) {
+        if (logz_out && s >= 1) logz_out[s - 1] = p[(size_t)s].logZ;
+        if (ess_out) ess_out[s] = p[(size_t)s].ess;
+        if (resampled_out) resampled_out[s] = (uint8_t)p[(size_t)s].resampled;
+    }
+    return APS_OK;
+}
+
+extern "C" int aps_get_states(aps_handle *h, int64_t t, double *x_out) {
+    NEED_SWEEP("aps_get_states");
+    const DevCtx &c = h->ctx;
+    if (!x_out || t < 1 || t > c.T) return fail(APS_ERR_INVALID, "aps_get_states: t out of range");
+    if (!h->cfg.keep_history && t < c.T - 1) return fail(APS_ERR_INVALID, "aps_get_states: history not kept");
+    std::vector<double> soa((size_t)c.N * c.d);
+    CU(cudaMemcpyAsync(soa.data(), c.x + ((t - 1) % c.x_slabs) * (long long)c.d * c.N, sizeof(double) * soa.size(),
+                       cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    for (long long i = 0; i < c.N; ++i)
+        for (int k = 0; k < c.d; ++k) x_out[i * c.d + k] = soa[(size_t)k * c.N + i];
+    return APS_OK;
+}
+
+extern "C" int aps_get_ancestors(aps_handle *h, int64_t t, int32_t *anc_out) {
+    NEED_SWEEP("aps_get_ancestors");
+    const DevCtx &c = h->ctx;
+    if (!anc_out || t < 2 || t > c.T + 1) return fail(APS_ERR_INVALID, "aps_get_ancestors: t must be in 2..T+1");
+    if (!h->cfg.keep_history && t < c.T) return fail(APS_ERR_INVALID, "aps_get_ancestors: history not kept");
+    CU(cudaMemcpyAsync(anc_out, c.anc + ((t - 1) % c.anc_slabs) * c.N, sizeof(int32_t) * (size_t)c.N,
+                       cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return APS_OK;
+}
+
+extern "C" int aps_last_sweep_ms(aps_handle *h, float *ms_out) {
+    NEED_SWEEP("aps_last_sweep_ms");
+    if (ms_out) *ms_out = h->last_ms;
+    return APS_OK;
+}
+
+extern "C" int aps_last_sweep_launches(aps_handle *h, int64_t *n_out) {
+    NEED_SWEEP("aps_last_sweep_launches");
+    if (n_out) *n_out = h->last_launches;
+    return APS_OK;
+}
+
+// ================================================================== operator level
+// A grow-only device workspace shared by the operator-level entry points (serialised by a mutex).
+struct OpWorkspace {
+    std::mutex mu;
+    cudaStream_t stream = nullptr;
+    long long cap_m = 0, cap_n = 0;
+    double *d_in = nullptr, *d_wout = nullptr;
+    u64 *d_q = nullptr, *tile_sum = nullptr, *tile_s1 = nullptr, *tile_s2 = nullptr, *tile_prefix = nullptr;
+    int32_t *d_idx32 = nullptr;
+    long long *d_idx64 = nullptr;
+    StepAcc *acc = nullptr;
+    StepPlan *plan = nullptr;
+    SweepState *st = nullptr;
+    SweepParams *sp = nullptr;
+};
+static OpWorkspace g_ws;
+
+static int ws_reserve(OpWorkspace &w, long long m, long long n) {
+    if (!w.stream) {
+        CU(cudaStreamCreateWithFlags(&w.stream, cudaStreamNonBlocking));
+        CU(cudaMalloc(&w.acc, sizeof(StepAcc)));
+        CU(cudaMalloc(&w.plan, sizeof(StepPlan)));
+        CU(cudaMalloc(&w.st, sizeof(SweepState)));
+        CU(cudaMalloc(&w.sp, sizeof(SweepParams)));
+    }
+    if (m > w.cap_m) {
+        cudaFree(w.d_in); cudaFree(w.d_wout); cudaFree(w.d_q);
+        cudaFree(w.tile_sum); cudaFree(w.tile_s1); cudaFree(w.tile_s2); cudaFree(w.tile_prefix);
+        w.cap_m = 0;
+        const long long nt = (m + APS_TILE - 1) / APS_TILE;
+        CU(cudaMalloc(&w.d_in, sizeof(double) * (size_t)m));
+        CU(cudaMalloc(&w.d_wout, sizeof(double) * (size_t)m));
+        CU(cudaMalloc(&w.d_q, sizeof(u64) * (size_t)m));
+        CU(cudaMalloc(&w.tile_sum, sizeof(u64) * (size_t)nt));
+        CU(cudaMalloc(&w.tile_s1, sizeof(u64) * (size_t)nt));
+        CU(cudaMalloc(&w.tile_s2, sizeof(u64) * (size_t)nt));
+        CU(cudaMalloc(&w.tile_prefix, sizeof(u64) * (size_t)nt));
+        w.cap_m = m;
+    }
+    if (n > w.cap_n) {
+        cudaFree(w.d_idx32); cudaFree(w.d_idx64);
+        w.cap_n = 0;
+        CU(cudaMalloc(&w.d_idx32, sizeof(int32_t) * (size_t)n));
+        CU(cudaMalloc(&w.d_idx64, sizeof(long long) * (size_t)n));
+        w.cap_n = n;
+    }
+    return APS_OK;
+}
+
+static bool is_device_ptr(const void *p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+static void op_ctx(OpWorkspace &w, DevCtx &c, long long m, long long n_draw) {
+    memset(&c, 0, sizeof(c));
+    c.q = w.d_q;
+    c.tile_sum = w.tile_sum;
+    c.tile_s1 = w.tile_s1;
+    c.tile_s2 = w.tile_s2;
+    c.tile_prefix = w.tile_prefix;
+    c.acc = w.acc;
+    c.plan = w.plan;
+    c.st = nullptr;
+    c.sp = w.sp;
+    c.anc = w.d_idx32;
+    c.N = m;
+    c.T = 0;
+    c.x_slabs = 1;
+    c.anc_slabs = 1;
+    c.num_tiles = (m + APS_TILE - 1) / APS_TILE;
+    c.d = 1;
+    c.dy = 1;
+    c.S = aps_weight_shift((uint64_t)m);
+    c.Hs = aps_ess_shift((uint64_t)m);
+    c.bare = 1;
+    c.ess_threshold = NAN;
+    c.logN = 0.0;
+    c.n_override = n_draw;
+}
+
+// max + normalise of a weight / log-weight vector into the workspace; fills *plan_host
+template <int INPUT>
+static int op_normalise(OpWorkspace &w, DevCtx &c, const double *in, long long m, uint64_t key, uint64_t ctr,
+                        StepPlan *plan_host) {
+    const double *d_in = in;
+    if (!is_device_ptr(in)) {
+        CU(cudaMemcpyAsync(w.d_in, in, sizeof(double) * (size_t)m, cudaMemcpyHostToDevice, w.stream));
+        d_in = w.d_in;
+    }
+    SweepParams sp;
+    sp.key = key;
+    sp.has_ref = 0;
+    sp.pad = 0;
+    CU(cudaMemcpyAsync(w.sp, &sp, sizeof(sp), cudaMemcpyHostToDevice, w.stream));
+    CU(cudaMemsetAsync(w.acc, 0, sizeof(StepAcc), w.stream));
+    k_vector_max<INPUT><<<stride_grid(m), APS_THREADS, 0, w.stream>>>(d_in, m, w.acc);
+    c.ctr_offset = (long long)ctr;
+    k_normalise<INPUT><<<(int)c.num_tiles, APS_THREADS, 0, w.stream>>>(c, d_in, 0);
+    CU(cudaMemcpyAsync(plan_host, w.plan, sizeof(StepPlan), cudaMemcpyDeviceToHost, w.stream));
+    CU(cudaStreamSynchronize(w.stream));
+    CU(cudaGetLastError());
+    return APS_OK;
+}
+
+extern "C" int aps_resample(int kind, const double *wts, int64_t m, int64_t n, uint64_t key, uint64_t ctr,
+                            int64_t *idx_out) {
+    if (!wts || !idx_out) return fail(APS_ERR_INVALID, "aps_resample: null argument");
+    if (m <= 0) return fail(APS_ERR_INVALID, "weight vector is empty");  // src/resampling.jl:103,154
+    if (m > 2147483647LL || n < 0 || n > 2147483647LL) return fail(APS_ERR_INVALID, "aps_resample: size out of range");
+    if (kind != APS_RESAMPLE_SYSTEMATIC && kind != APS_RESAMPLE_STRATIFIED)
+        return fail(APS_ERR_INVALID, "aps_resample: multinomial / residual are not built yet");
+    if (ctr >= (1ull << 40)) return fail(APS_ERR_INVALID, "aps_resample: ctr must be < 2^40");
+    if (n == 0) return APS_OK;
+    OpWorkspace &w = g_ws;
+    std::lock_guard<std::mutex> lock(w.mu);
+    int rc = ws_reserve(w, m, n);
+    if (rc) return rc;
+    DevCtx c;
+    op_ctx(w, c, m, n);
+    StepPlan p;
+    rc = op_normalise<IN_W>(w, c, wts, m, key, ctr, &p);
+    if (rc) return rc;
+    if (p.err) return fail(APS_ERR_WEIGHTS, "sample could not be selected (are the weights normalized?)");
+    pick_resample(kind)<<<(int)c.num_tiles, APS_THREADS, 0, w.stream>>>(c, 0);
+    const bool dev_out = is_device_ptr(idx_out);
+    long long *d_out = dev_out ? (long long *)idx_out : w.d_idx64;
+    k_to_one_based<<<stride_grid(n), APS_THREADS, 0, w.stream>>>(w.d_idx32, n, d_out);
+    if (!dev_out) CU(cudaMemcpyAsync(idx_out, w.d_idx64, sizeof(long long) * (size_t)n, cudaMemcpyDeviceToHost, w.stream));
+    CU(cudaStreamSynchronize(w.stream));
+    CU(cudaGetLastError());
+    return APS_OK;
+}
+
+static int op_logw(const double *logw, int64_t n, StepPlan *p, OpWorkspace &w, DevCtx &c) {
+    if (!logw) return fail(APS_ERR_INVALID, "null log-weight vector");
+    if (n <= 0 || n > 2147483647LL) return fail(APS_ERR_INVALID, "log-weight vector is empty or too long");
+    int rc = ws_reserve(w, n, 1);
+    if (rc) return rc;
+    op_ctx(w, c, n, 0);
+    return op_normalise<IN_LOGW>(w, c, logw, n, 0, 0, p);
+}
+
+extern "C" int aps_logsumexp(const double *logw, int64_t n, double *out) {
+    OpWorkspace &w = g_ws;
+    std::lock_guard<std::mutex> lock(w.mu);
+    DevCtx c;
+    StepPlan p;
+    int rc = op_logw(logw, n, &p, w, c);
+    if (rc) return rc;
+    if (p.err) {
+        if (p.M == -INFINITY) {  // logsumexp of all -Inf is -Inf, not an error
+            *out = -INFINITY;
+            return APS_OK;
+        }
+        return fail(APS_ERR_WEIGHTS, "aps_logsumexp: NaN or +Inf log-weight");
+    }
+    *out = p.logZ;
+    return APS_OK;
+}
+
+extern "C" int aps_ess(const double *logw, int64_t n, double *out) {
+    OpWorkspace &w = g_ws;
+    std::lock_guard<std::mutex> lock(w.mu);
+    DevCtx c;
+    StepPlan p;
+    int rc = op_logw(logw, n, &p, w, c);
+    if (rc) return rc;
+    if (p.err) return fail(APS_ERR_WEIGHTS, "aps_ess: weights not normalisable");
+    *out = p.ess;
+    return APS_OK;
+}
+
+extern "C" int aps_softmax(const double *logw, int64_t n, double *w_out) {
+    if (!w_out) return fail(APS_ERR_INVALID, "aps_softmax: null output");
+    OpWorkspace &w = g_ws;
+    std::lock_guard<std::mutex> lock(w.mu);
+    DevCtx c;
+    StepPlan p;
+    int rc = op_logw(logw, n, &p, w, c);
+    if (rc) return rc;
+    if (p.err) return fail(APS_ERR_WEIGHTS, "aps_softmax: weights not normalisable");
+    const bool dev_out = is_device_ptr(w_out);
+    double *d_out = dev_out ? w_out : w.d_wout;
+    k_weights_out<<<stride_grid(n), APS_THREADS, 0, w.stream>>>(w.d_q, w.plan, n, c.S, 0, d_out);
+    if (!dev_out) CU(cudaMemcpyAsync(w_out, w.d_wout, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, w.stream));
+    CU(cudaStreamSynchronize(w.stream));
+    CU(cudaGetLastError());
+    return APS_OK;
+}
+
+extern "C" int aps_randcat(const double *wts, int64_t n, uint64_t key, uint64_t ctr, int64_t *idx_out) {
+    if (!wts || !idx_out) return fail(APS_ERR_INVALID, "aps_randcat: null argument");
+    if (n <= 0 || n > 2147483647LL) return fail(APS_ERR_INVALID, "weight vector is empty");
+    if (ctr >= (1ull << 40)) return fail(APS_ERR_INVALID, "aps_randcat: ctr must be < 2^40");
+    OpWorkspace &w = g_ws;
+    std::lock_guard<std::mutex> lock(w.mu);
+    int rc = ws_reserve(w, n, 1);
+    if (rc) return rc;
+    DevCtx c;
+    op_ctx(w, c, n, 1);
+    StepPlan p;
+    rc = op_normalise<IN_W>(w, c, wts, n, key, ctr, &p);
+    if (rc) return rc;
+    if (p.err) return fail(APS_ERR_WEIGHTS, "aps_randcat: weights not normalisable");
+    // force the non-uniform branch of k_pick: it reads plan[0].resampled
+    StepPlan p2 = p;
+    p2.resampled = 0;
+    CU(cudaMemcpyAsync(w.plan, &p2, sizeof(p2), cudaMemcpyHostToDevice, w.stream));
+    DevCtx cc = c;
+    cc.st = w.st;
+    SweepState st0;
+    memset(&st0, 0, sizeof(st0));
+    st0.picked_slot = -1;
+    CU(cudaMemcpyAsync(w.st, &st0, sizeof(st0), cudaMemcpyHostToDevice, w.stream));
+    k_pick<<<1, APS_THREADS, 0, w.stream>>>(cc, 0, (long long)ctr, APS_DOM_RESAMPLE);
+    CU(cudaMemcpyAsync(&st0, w.st, sizeof(st0), cudaMemcpyDeviceToHost, w.stream));
+    CU(cudaStreamSynchronize(w.stream));
+    CU(cudaGetLastError());
+    if (st0.picked_slot < 0) return fail(APS_ERR_WEIGHTS, "aps_randcat: no index could be selected");
+    *idx_out = st0.picked_slot + 1;
+    return APS_OK;
+}
+
+// ================================================================== micro-benchmark of the resample kernel
+extern "C" int aps_bench_resample(int kind, int64_t n, int iters, int flush_l2, uint64_t seed, float *avg_ms_out,
+                                  float *min_ms_out) {
+    if (n <= 0 || n > 2147483647LL || iters < 1) return fail(APS_ERR_INVALID, "aps_bench_resample: bad size");
+    if (kind != APS_RESAMPLE_SYSTEMATIC && kind != APS_RESAMPLE_STRATIFIED)
+        return fail(APS_ERR_INVALID, "aps_bench_resample: kind not built yet");
+    OpWorkspace &w = g_ws;
+    std::lock_guard<std::mutex> lock(w.mu);
+    int rc = ws_reserve(w, n, n);
+    if (rc) return rc;
+    DevCtx c;
+    op_ctx(w, c, n, n);
+    SweepParams sp;
+    sp.key = seed;
+    sp.has_ref = 0;
+    sp.pad = 0;
+    CU(cudaMemcpyAsync(w.sp, &sp, sizeof(sp), cudaMemcpyHostToDevice, w.stream));
+    CU(cudaMemsetAsync(w.acc, 0, sizeof(StepAcc), w.stream));
+    k_bench_weights<<<stride_grid(n), APS_THREADS, 0, w.stream>>>(w.d_q, n, c.S, seed);
+    k_normalise<IN_Q><<<(int)c.num_tiles, APS_THREADS, 0, w.stream>>>(c, nullptr, 0);
+    StepPlan p;
+    CU(cudaMemcpyAsync(&p, w.plan, sizeof(p), cudaMemcpyDeviceToHost, w.stream));
+    CU(cudaStreamSynchronize(w.stream));
+    CU(cudaGetLastError());
+    if (p.err) return fail(APS_ERR_WEIGHTS, "aps_bench_resample: synthetic weights not normalisable");
+    void *flush = nullptr;
+    const size_t flush_bytes = 512ull << 20;
+    if (flush_l2) CU(cudaMalloc(&flush, flush_bytes));
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0));
+    CU(cudaEventCreate(&e1));
+    step_fn f = pick_resample(kind);
+    float tot = 0.f, mn = 1e30f;
+    for (int it = -3; it < iters; ++it) {  // 3 warm-up launches
+        if (flush_l2) CU(cudaMemsetAsync(flush, it & 0xff, flush_bytes, w.stream));
+        CU(cudaEventRecord(e0, w.stream));
+        f<<<(int)c.num_tiles, APS_THREADS, 0, w.stream>>>(c, 0);
+        CU(cudaEventRecord(e1, w.stream));
+        CU(cudaStreamSynchronize(w.stream));
+        float ms = 0.f;
+        CU(cudaEventElapsedTime(&ms, e0, e1));
+        if (it >= 0) {
+            tot += ms;
+            mn = ms < mn ? ms : mn;
+        }
+    }
+    CU(cudaGetLastError());
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    if (flush) cudaFree(flush);
+    if (avg_ms_out) *avg_ms_out = tot / iters;
+    if (min_ms_out) *min_ms_out = mn;
+    return APS_OK;
+}
+
+// ================================================================== multi-GPU plumbing (not built yet)
+extern "C" int aps_ipc_export(aps_handle *h, uint8_t *blob_out) {
+    (void)h;
+    (void)blob_out;
+    return fail(APS_ERR_COMM, "aps_ipc_export: multi-GPU sharding is not built yet");
+}
+extern "C" int aps_ipc_import(aps_handle *h, const uint8_t *blobs) {
+    (void)h;
+    (void)blobs;
+    return fail(APS_ERR_COMM, "aps_ipc_import: multi-GPU sharding is not built yet");
+}

@@ -1,0 +1,687 @@
+// aps_kernels.cuh -- the per-time-step hot path as sm_100a CUDA kernels.
+//
+//   k_propagate   (K1)  reweight!/advance!           src/container.jl:259-302, src/pgas.jl:53-89
+//   k_normalise   (K2)  getweights/logZ/ESS + the ESS decision and evidence accumulation
+//                                                     src/container.jl:95-119,233-251,332-359
+//   k_resample    (K3)  resample_systematic / resample_stratified + "children grouped by parent"
+//                                                     src/resampling.jl:98-183, src/container.jl:182-217
+//   k_select_*    (K4/K5) one categorical draw: PGAS ancestor (src/pgas.jl:113-128) and the final
+//                        pick (src/container.jl:33-36)
+//   k_backtrace         trajectory extraction through the ancestor store (replaces the deep
+//                        copies of fork, src/pgas.jl:99-104)
+//
+// All reductions that feed a comparison are exact integer sums (see aps_math.h), so results do
+// not depend on tile size, block scheduling or the number of GPUs.
+#pragma once
+#include "aps_device.cuh"
+
+struct SweepParams {
+    u64 key;      // master seed of this sweep
+    int has_ref;  // conditional sweep (PG / PGAS with a retained trajectory)
+    int pad;
+};
+
+struct DevCtx {
+    aps_model_dev md;
+    double *x;
+    int32_t *anc;
+    double *logw;
+    u64 *q;
+    u64 *tile_sum, *tile_s1, *tile_s2, *tile_prefix;
+    StepAcc *acc;
+    StepPlan *plan;
+    SweepState *st;
+    const double *Y;
+    const double *ref;
+    const SweepParams *sp;
+    long long N, T;
+    long long x_slabs, anc_slabs;
+    long long num_tiles;
+    int d, dy;
+    int S, Hs;     // weight shift, ESS shift
+    int sampler, resampler;
+    int bare;      // bare resampler function: resample at every step
+    int pad;
+    double ess_threshold;
+    double logN;
+    long long n_override;  // operator level: number of indices to draw (0: N, or N-1 with a reference)
+    long long ctr_offset;  // operator level: Philox step counter = plan index + ctr_offset
+};
+
+enum { IN_LOGW = 0, IN_W = 1, IN_Q = 2 };
+
+// ---------------------------------------------------------------- init: decision point s = 0
+// All log-weights are zero: ESS = N exactly, logZ = log N; particles carry no state yet, so the
+// initial resample_propagate! (src/container.jl:325) only decides `resampled[0]`.
+__global__ void k_init_sweep(const __grid_constant__ DevCtx c) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        StepPlan p;
+        p.M = 0.0;
+        p.logZ = c.logN;
+        p.ess = (double)c.N;
+        p.Q = (u64)c.N << c.S;
+        p.R = 0;
+        p.ratio = 0.0;
+        p.roff = 0.0;
+        p.n = c.N - (c.sp->has_ref ? 1 : 0);
+        p.resampled = c.bare ? 1 : ((double)c.N <= c.ess_threshold * (double)c.N ? 1 : 0);
+        p.err = 0;
+        c.plan[0] = p;
+        c.st->logev = 0.0;
+        c.st->err = 0;
+        c.st->picked_slot = -1;
+    }
+}
+
+// ---------------------------------------------------------------- K1: propagate + reweight
+template <int D, int OBS>
+__global__ void __launch_bounds__(APS_THREADS) k_propagate(const __grid_constant__ DevCtx c, const long long t) {
+    __shared__ u64 red[APS_THREADS / 32];
+    const long long N = c.N;
+    const bool reset = c.plan[t - 1].resampled != 0;
+    const int has_ref = c.sp->has_ref;
+    const u64 key = c.sp->key;
+    double *__restrict__ xt = c.x + ((t - 1) % c.x_slabs) * (long long)D * N;
+    const double *__restrict__ xp = c.x + ((t + c.x_slabs - 2) % c.x_slabs) * (long long)D * N;
+    const int32_t *__restrict__ anc = c.anc + ((t - 1) % c.anc_slabs) * N;
+    double y[APS_MAX_D];
+#pragma unroll
+    for (int m = 0; m < APS_MAX_D; ++m) y[m] = m < c.dy ? c.Y[(t - 1) * c.dy + m] : 0.0;
+
+    u64 bmax = 0;
+    unsigned bad = 0;
+    for (long long i = (long long)blockIdx.x * APS_THREADS + threadIdx.x; i < N;
+         i += (long long)gridDim.x * APS_THREADS) {
+        double x[D];
+        if (has_ref && i == N - 1) {
+#pragma unroll
+            for (int k = 0; k < D; ++k) x[k] = c.ref[(t - 1) * D + k];
+        } else {
+            double z[D + 1];
+            aps_state_normals<D>(key, (u64)i, (u64)t, z);
+            if (t == 1) {
+                aps_prior_draw<D>(&c.md, z, x);
+            } else {
+                const long long a = anc[i];
+                double xpv[D];
+#pragma unroll
+                for (int k = 0; k < D; ++k) xpv[k] = xp[(long long)k * N + a];
+                aps_trans_draw<D>(&c.md, xpv, z, x);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < D; ++k) xt[(long long)k * N + i] = x[k];
+        const double ll = aps_obs_logpdf<D, OBS>(&c.md, x, y);
+        const double lw = (reset ? 0.0 : c.logw[i]) + ll;
+        c.logw[i] = lw;
+        if (lw != lw) bad = 1;
+        else {
+            const u64 e = aps_encode_ordered(lw);
+            bmax = e > bmax ? e : bmax;
+        }
+    }
+    bmax = block_max_u64(bmax, red);
+    bad = __syncthreads_or(bad);
+    if (threadIdx.x == 0) {
+        if (bmax) atomicMax(&c.acc[t].max_enc, bmax);
+        if (bad) atomicOr(&c.acc[t].bad, 1u);
+    }
+}
+
+// max of a plain vector (operator-level entry points)
+template <int INPUT>
+__global__ void __launch_bounds__(APS_THREADS) k_vector_max(const double *__restrict__ in, long long n, StepAcc *acc) {
+    __shared__ u64 red[APS_THREADS / 32];
+    u64 bmax = 0;
+    unsigned bad = 0;
+    for (long long i = (long long)blockIdx.x * APS_THREADS + threadIdx.x; i < n;
+         i += (long long)gridDim.x * APS_THREADS) {
+        const double v = in[i];
+        if (v != v || (INPUT == IN_W && v < 0.0)) bad = 1;
+        else {
+            const u64 e = aps_encode_ordered(v);
+            bmax = e > bmax ? e : bmax;
+        }
+    }
+    bmax = block_max_u64(bmax, red);
+    bad = __syncthreads_or(bad);
+    if (threadIdx.x == 0) {
+        if (bmax) atomicMax(&acc->max_enc, bmax);
+        if (bad) atomicOr(&acc->bad, 1u);
+    }
+}
+
+// ---------------------------------------------------------------- K2: normalise
+// One tile of APS_TILE particles per block: q_i = floor(exp(logw_i - M) 2^S), tile totals of q,
+// (q >> Hs) and (q >> Hs)^2. The last block to finish scans the tile totals and writes the plan
+// of decision point s: logZ, ESS, the resampling decision, the systematic offset, the evidence.
+template <int INPUT>
+__global__ void __launch_bounds__(APS_THREADS) k_normalise(const __grid_constant__ DevCtx c, const double *__restrict__ in,
+                                                           const long long s) {
+    __shared__ u64 red[APS_THREADS / 32];
+    __shared__ unsigned s_last;
+    const long long N = c.N;
+    const long long base = (long long)blockIdx.x * APS_TILE;
+    StepAcc *acc = &c.acc[s];
+    const double M = aps_decode_ordered(acc->max_enc);
+    const double scale = aps_pow2i(c.S);
+    u64 s0 = 0, s1 = 0, s2 = 0;
+#pragma unroll
+    for (int r = 0; r < APS_IPT; ++r) {
+        const long long i = base + r * APS_THREADS + threadIdx.x;
+        if (i < N) {
+            u64 qi;
+            if (INPUT == IN_Q) {
+                qi = c.q[i];
+            } else {
+                double e;
+                if (INPUT == IN_LOGW) e = aps_exp(in[i] - M);
+                else e = in[i] / M;
+                qi = (e > 0.0) ? (u64)__double2ull_rz(e * scale) : 0ull;
+                c.q[i] = qi;
+            }
+            const u64 qs = qi >> c.Hs;
+            s0 += qi;
+            s1 += qs;
+            s2 += qs * qs;
+        }
+    }
+    s0 = block_sum_u64(s0, red);
+    s1 = block_sum_u64(s1, red);
+    s2 = block_sum_u64(s2, red);
+    if (threadIdx.x == 0) {
+        c.tile_sum[blockIdx.x] = s0;
+        c.tile_s1[blockIdx.x] = s1;
+        c.tile_s2[blockIdx.x] = s2;
+        __threadfence();
+        const unsigned ticket = atomicAdd(&acc->done_ctr, 1u);
+        s_last = (ticket == gridDim.x - 1) ? 1u : 0u;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+
+    // ---- last block: exclusive scan of the tile totals (each thread owns a contiguous chunk)
+    const long long nt = c.num_tiles;
+    const long long per = (nt + APS_THREADS - 1) / APS_THREADS;
+    const long long lo = (long long)threadIdx.x * per;
+    const long long hi = lo + per < nt ? lo + per : nt;
+    u64 a0 = 0, a1 = 0, a2 = 0;
+    for (long long k = lo; k < hi; ++k) {
+        a0 += __ldcg(&c.tile_sum[k]);
+        a1 += __ldcg(&c.tile_s1[k]);
+        a2 += __ldcg(&c.tile_s2[k]);
+    }
+    u64 Q;
+    u64 run = block_excl_scan_u64(a0, red, &Q);
+    for (long long k = lo; k < hi; ++k) {
+        c.tile_prefix[k] = run;
+        run += __ldcg(&c.tile_sum[k]);
+    }
+    const u64 Q1 = block_sum_u64(a1, red);
+    const u64 Q2 = block_sum_u64(a2, red);
+    if (threadIdx.x == 0) {
+        StepPlan p;
+        int err = 0;
+        if (acc->bad) err = APS_ERR_WEIGHTS;
+        if (INPUT != IN_Q) {
+            if (acc->max_enc == 0) err = APS_ERR_WEIGHTS;
+            if (!(M == M) || M == aps_bits2d(0x7FF0000000000000ULL) || M == aps_bits2d(0xFFF0000000000000ULL))
+                err = APS_ERR_WEIGHTS;
+            if (INPUT == IN_W && !(M > 0.0)) err = APS_ERR_WEIGHTS;
+        }
+        if (Q == 0 || Q2 == 0) err = APS_ERR_WEIGHTS;
+        p.M = M;
+        p.Q = Q;
+        p.logZ = M + aps_log((double)Q * aps_pow2i(-c.S));
+        p.ess = ((double)Q1 * (double)Q1) / (double)Q2;
+        p.resampled = c.bare ? 1 : (p.ess <= c.ess_threshold * (double)N ? 1 : 0);
+        p.n = c.n_override > 0 ? c.n_override : N - (c.sp->has_ref ? 1 : 0);
+        uint64_t w0, w1;
+        aps_philox2x64(0, aps_ctr1((u64)(s + c.ctr_offset), APS_DOM_RESAMPLE, 0), c.sp->key, &w0, &w1);
+        p.R = ceil_uq53(aps_u53(w0), Q);
+        p.ratio = (double)p.n / (double)Q;
+        p.roff = (double)p.R / (double)Q;
+        p.err = err;
+        if (c.st) {
+            if (err) c.st->err = err;
+            else if (s >= 1) {
+                const StepPlan &pv = c.plan[s - 1];
+                const double logZ0 = pv.resampled ? c.logN : pv.logZ;  // logZ(pc) after resample_propagate!
+                c.st->logev += p.logZ - logZ0;                         // src/container.jl:341,359
+            }
+        }
+        c.plan[s] = p;
+    }
+}
+
+// ---------------------------------------------------------------- K3: resample
+// K(C) = #{ children i in [0,n) : i Q + R_i <= C n }: the number of children whose threshold lies
+// at or below cumulative weight C. Parent j owns children [K(C_{j-1}), K(C_j)).
+__device__ __forceinline__ bool thr_le(u64 i, u64 Q, u64 R, u128 Cn) {
+    return le_128(add_128_64(mul_64_64(i, Q), R), Cn);
+}
+
+// first i in [0,n] with !(i < n && i Q + R <= C n), starting from a guess k
+__device__ __noinline__ long long first_above_exact(long long k, u64 C, u64 Q, u64 R, long long n) {
+    const u128 Cn = mul_64_64(C, (u64)n);
+    if (k < 0) k = 0;
+    if (k > n) k = n;
+    long long lo = k - 2 < 0 ? 0 : k - 2, hi = k + 2 > n ? n : k + 2;
+    if (lo > 0 && !thr_le((u64)(lo - 1), Q, R, Cn)) lo = 0;
+    if (hi < n && thr_le((u64)hi, Q, R, Cn)) hi = n;
+    while (lo < hi) {
+        const long long mid = (lo + hi) >> 1;
+        if (thr_le((u64)mid, Q, R, Cn)) lo = mid + 1;
+        else hi = mid;
+    }
+    return lo;
+}
+
+#define APS_KEPS 0x1.0p-10
+
+__device__ __forceinline__ long long first_above(double est, u64 C, u64 Q, u64 R, long long n) {
+    // est approximates (C n - R) / Q to ~2^-19 absolute; accept floor(est)+1 unless est is within
+    // APS_KEPS of an integer, in which case the count is settled with exact 128-bit arithmetic.
+    if (est > -4.0e18 && est < 4.0e18) {
+        const double kf = floor(est);
+        const double fr = est - kf;
+        long long k = (long long)kf + 1;
+        if (fr > APS_KEPS && fr < 1.0 - APS_KEPS) return k < 0 ? 0 : (k > n ? n : k);
+        return first_above_exact(k, C, Q, R, n);
+    }
+    return first_above_exact(0, C, Q, R, n);
+}
+
+template <int KIND>
+__device__ __forceinline__ long long children_below(u64 C, const StepPlan &p, u64 key, u64 s) {
+    if (KIND == APS_RESAMPLE_SYSTEMATIC) {
+        return first_above((double)C * p.ratio - p.roff, C, p.Q, p.R, p.n);
+    } else {  // stratified: child i draws its own offset R_i; only stratum i* = floor(C n / Q) is undecided
+        const long long n = p.n;
+        const long long F = first_above((double)C * p.ratio, C, p.Q, 0ull, n);
+        const u128 Cn = mul_64_64(C, (u64)n);
+        if (F == n && le_128(mul_64_64((u64)n, p.Q), Cn)) return n;
+        const long long istar = F - 1;
+        uint64_t w0, w1;
+        aps_philox2x64((u64)istar, aps_ctr1(s, APS_DOM_RESAMPLE, 0), key, &w0, &w1);
+        const u64 Ri = ceil_uq53(aps_u53(w0), p.Q);
+        return istar + (thr_le((u64)istar, p.Q, Ri, Cn) ? 1 : 0);
+    }
+}
+
+// Expand phase shared by all resamplers: thread-blocked child ranges [klo_j, khi_j) of the
+// tile's parents -> sorted ancestor indices, staged through shared memory with a max-scan
+// (load-balanced: cost depends on the number of children, not on how skewed the weights are).
+__device__ __forceinline__ void expand_tile(const long long *khi, long long klo0, long long kA, long long kB,
+                                            long long base, int32_t *__restrict__ anc_out, int *own, int *wmax) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (long long cb = kA; cb < kB; cb += APS_CAP) {
+        const int cnt = (int)((kB - cb) < APS_CAP ? (kB - cb) : APS_CAP);
+        for (int p = tid; p < cnt; p += APS_THREADS) own[p] = 0;
+        __syncthreads();
+        long long klo = klo0;
+#pragma unroll
+        for (int j = 0; j < APS_IPT; ++j) {
+            const long long kh = khi[j];
+            if (klo < kh && kh > cb && klo < cb + cnt) {
+                const long long pos = (klo > cb ? klo : cb) - cb;
+                own[pos] = tid * APS_IPT + j + 1;
+            }
+            klo = kh;
+        }
+        __syncthreads();
+        int v[APS_CPT];
+        int run = 0;
+#pragma unroll
+        for (int m = 0; m < APS_CPT; ++m) {
+            const int p = tid * APS_CPT + m;
+            const int o = p < cnt ? own[p] : 0;
+            run = o > run ? o : run;
+            v[m] = run;
+        }
+        int inc = run;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int tt = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc = tt > inc ? tt : inc;
+        }
+        if (lane == 31) wmax[warp] = inc;
+        int excl = __shfl_up_sync(0xffffffffu, inc, 1);
+        if (lane == 0) excl = 0;
+        __syncthreads();
+#pragma unroll
+        for (int w = 0; w < APS_THREADS / 32; ++w)
+            if (w < warp) excl = wmax[w] > excl ? wmax[w] : excl;
+#pragma unroll
+        for (int m = 0; m < APS_CPT; ++m) {
+            const int p = tid * APS_CPT + m;
+            if (p < cnt) own[p] = v[m] > excl ? v[m] : excl;
+        }
+        __syncthreads();
+        for (int p = tid; p < cnt; p += APS_THREADS) anc_out[cb + p] = (int32_t)(base + own[p] - 1);
+        __syncthreads();
+    }
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(APS_THREADS) k_resample(const __grid_constant__ DevCtx c, const long long s) {
+    __shared__ u64 red[APS_THREADS / 32];
+    __shared__ long long wlast[APS_THREADS / 32];
+    __shared__ long long s_k[2];
+    __shared__ int own[APS_CAP];
+    __shared__ int wmax[APS_THREADS / 32];
+    const long long N = c.N;
+    const StepPlan &p = c.plan[s];
+    int32_t *__restrict__ anc_out = c.anc + (s % c.anc_slabs) * N;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const long long base = (long long)blockIdx.x * APS_TILE;
+
+    if (!p.resampled || p.err) {
+        // update_keys! branch (src/container.jl:247): every particle continues, weights kept
+#pragma unroll
+        for (int r = 0; r < APS_IPT; ++r) {
+            const long long i = base + r * APS_THREADS + tid;
+            if (i < N) anc_out[i] = (int32_t)i;
+        }
+        return;
+    }
+
+    // ---- load 8 consecutive integer weights per thread, local inclusive sums
+    u64 cum[APS_IPT];
+    const long long i0 = base + (long long)tid * APS_IPT;
+    if (base + APS_TILE <= N) {
+        const ulonglong2 *src = reinterpret_cast<const ulonglong2 *>(c.q + i0);
+#pragma unroll
+        for (int r = 0; r < APS_IPT / 2; ++r) {
+            const ulonglong2 v = __ldg(src + r);
+            cum[2 * r] = v.x;
+            cum[2 * r + 1] = v.y;
+        }
+    } else {
+#pragma unroll
+        for (int r = 0; r < APS_IPT; ++r) cum[r] = (i0 + r < N) ? c.q[i0 + r] : 0ull;
+    }
+#pragma unroll
+    for (int r = 1; r < APS_IPT; ++r) cum[r] += cum[r - 1];
+    u64 tile_total;
+    const u64 excl = block_excl_scan_u64(cum[APS_IPT - 1], red, &tile_total) + c.tile_prefix[blockIdx.x];
+
+    // ---- children counts below each inclusive cumulative weight
+    const u64 key = c.sp->key;
+    long long khi[APS_IPT];
+#pragma unroll
+    for (int r = 0; r < APS_IPT; ++r) khi[r] = children_below<KIND>(excl + cum[r], p, key, (u64)(s + c.ctr_offset));
+    long long klo0 = __shfl_up_sync(0xffffffffu, khi[APS_IPT - 1], 1);
+    if (lane == 31) wlast[warp] = khi[APS_IPT - 1];
+    if (tid == 0) {
+        const long long kA = blockIdx.x == 0 ? 0 : children_below<KIND>(excl, p, key, (u64)(s + c.ctr_offset));
+        s_k[0] = kA;
+    }
+    if (tid == APS_THREADS - 1) s_k[1] = khi[APS_IPT - 1];
+    __syncthreads();
+    if (lane == 0) klo0 = warp == 0 ? s_k[0] : wlast[warp - 1];
+    const long long kA = s_k[0], kB = s_k[1];
+
+    expand_tile(khi, klo0, kA, kB, base, anc_out, own, wmax);
+
+    // reference particle keeps the last slot (src/container.jl:219-224); PGAS may overwrite it
+    if (blockIdx.x == gridDim.x - 1 && tid == 0 && p.n < N) anc_out[N - 1] = (int32_t)(N - 1);
+}
+
+// ---------------------------------------------------------------- categorical draw (PGAS ancestor, final pick)
+// lw_i for the PGAS ancestor weights: log f(X_ref[c-1] | X_i[c-2]) + logW_i   (src/pgas.jl:26-46)
+template <int D>
+__device__ __forceinline__ double pgas_logweight(const DevCtx &c, long long s, long long i) {
+    const long long N = c.N;
+    const double *xpp = c.x + ((s - 2) % c.x_slabs) * (long long)D * N;   // states of time s-1 (= c-2)
+    const int32_t *anc_cur = c.anc + ((s - 1) % c.anc_slabs) * N;         // ancestors of set s (= c-1)
+    const long long a = anc_cur[i];
+    double xp[D], xr[D];
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+        xp[k] = xpp[(long long)k * N + a];
+        xr[k] = c.ref[(s - 1) * D + k];                                   // X_ref[c-1], c = s+1
+    }
+    return aps_trans_logpdf<D>(&c.md, xp, xr) + c.logw[i];
+}
+
+__device__ __forceinline__ bool pgas_active(const DevCtx &c, long long s) {
+    // update_ref! (src/pgas.jl:113-128) runs inside resample_propagate! only when resampling
+    // happens, the reference counter c = s+1 is > 2 and the model is not done (c <= T).
+    return c.sampler == APS_PGAS && c.sp->has_ref && s >= 2 && s <= c.T - 1 && c.plan[s].resampled &&
+           !c.plan[s].err;
+}
+
+template <int D>
+__global__ void __launch_bounds__(APS_THREADS) k_pgas_max(const __grid_constant__ DevCtx c, const long long s) {
+    __shared__ u64 red[APS_THREADS / 32];
+    if (!pgas_active(c, s)) return;
+    u64 bmax = 0;
+    unsigned bad = 0;
+    for (long long i = (long long)blockIdx.x * APS_THREADS + threadIdx.x; i < c.N;
+         i += (long long)gridDim.x * APS_THREADS) {
+        const double lw = pgas_logweight<D>(c, s, i);
+        if (lw != lw) bad = 1;
+        else {
+            const u64 e = aps_encode_ordered(lw);
+            bmax = e > bmax ? e : bmax;
+        }
+    }
+    bmax = block_max_u64(bmax, red);
+    bad = __syncthreads_or(bad);
+    if (threadIdx.x == 0) {
+        if (bmax) atomicMax(&c.acc[s].sel_max_enc, bmax);
+        if (bad) atomicOr(&c.acc[s].bad, 2u);
+    }
+}
+
+// find the first element j of a tile with (prefix + inclusive_sum_j) > tau; all threads return it
+// (or -1). Each thread supplies its 8 consecutive weights.
+__device__ __forceinline__ int tile_find_first_above(const u64 *w8, u64 prefix, u64 tau, u64 *red, int *s_found) {
+    u64 cum[APS_IPT];
+    cum[0] = w8[0];
+#pragma unroll
+    for (int r = 1; r < APS_IPT; ++r) cum[r] = cum[r - 1] + w8[r];
+    u64 tot;
+    const u64 excl = block_excl_scan_u64(cum[APS_IPT - 1], red, &tot) + prefix;
+    if (threadIdx.x == 0) *s_found = 0x7fffffff;
+    __syncthreads();
+    int mine = 0x7fffffff;
+#pragma unroll
+    for (int r = APS_IPT - 1; r >= 0; --r)
+        if (excl + cum[r] > tau) mine = threadIdx.x * APS_IPT + r;
+    if (mine != 0x7fffffff) atomicMin(s_found, mine);
+    __syncthreads();
+    const int f = *s_found;
+    return f == 0x7fffffff ? -1 : f;
+}
+
+// PGAS: tile totals of the quantised ancestor weights; the last block locates the drawn tile,
+// rescans it and rewires the reference's ancestor pointer (the splice of src/pgas.jl:125-127).
+template <int D>
+__global__ void __launch_bounds__(APS_THREADS) k_pgas_select(const __grid_constant__ DevCtx c, const long long s) {
+    __shared__ u64 red[APS_THREADS / 32];
+    __shared__ unsigned s_last;
+    __shared__ long long s_tile;
+    __shared__ u64 s_pref, s_tau;
+    __shared__ int s_found;
+    if (!pgas_active(c, s)) return;
+    const long long N = c.N;
+    StepAcc *acc = &c.acc[s];
+    const double M = aps_decode_ordered(acc->sel_max_enc);
+    const double scale = aps_pow2i(c.S);
+    const long long base = (long long)blockIdx.x * APS_TILE;
+    u64 s0 = 0;
+#pragma unroll
+    for (int r = 0; r < APS_IPT; ++r) {
+        const long long i = base + r * APS_THREADS + threadIdx.x;
+        if (i < N) {
+            const double e = aps_exp(pgas_logweight<D>(c, s, i) - M);
+            s0 += (e > 0.0) ? (u64)__double2ull_rz(e * scale) : 0ull;
+        }
+    }
+    s0 = block_sum_u64(s0, red);
+    // tile_s1 is free at this point of the step (the plan of s is already written)
+    if (threadIdx.x == 0) {
+        c.tile_s1[blockIdx.x] = s0;
+        __threadfence();
+        const unsigned ticket = atomicAdd(&acc->sel_done_ctr, 1u);
+        s_last = (ticket == gridDim.x - 1) ? 1u : 0u;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    const long long nt = c.num_tiles;
+    const long long per = (nt + APS_THREADS - 1) / APS_THREADS;
+    const long long lo = (long long)threadIdx.x * per;
+    const long long hi = lo + per < nt ? lo + per : nt;
+    u64 a0 = 0;
+    for (long long k = lo; k < hi; ++k) a0 += __ldcg(&c.tile_s1[k]);
+    u64 Qs;
+    u64 run = block_excl_scan_u64(a0, red, &Qs);
+    if (threadIdx.x == 0) {
+        s_tile = -1;
+        uint64_t w0, w1;
+        aps_philox2x64(0, aps_ctr1((u64)s, APS_DOM_PGAS, 0), c.sp->key, &w0, &w1);
+        s_tau = floor_uq53(aps_u53(w0), Qs);
+        const double Mv = M;
+        if (acc->bad & 2u || Qs == 0 || !(Mv == Mv) || Mv == aps_bits2d(0xFFF0000000000000ULL)) c.st->err = APS_ERR_WEIGHTS;
+    }
+    __syncthreads();
+    const u64 tau = s_tau;
+    if (Qs == 0) return;
+    for (long long k = lo; k < hi; ++k) {
+        const u64 t = __ldcg(&c.tile_s1[k]);
+        if (run <= tau && tau < run + t) {
+            s_tile = k;
+            s_pref = run;
+        }
+        run += t;
+    }
+    __syncthreads();
+    const long long tile = s_tile;
+    if (tile < 0) return;
+    u64 w8[APS_IPT];
+#pragma unroll
+    for (int r = 0; r < APS_IPT; ++r) {
+        const long long i = tile * APS_TILE + (long long)threadIdx.x * APS_IPT + r;
+        w8[r] = 0;
+        if (i < N) {
+            const double e = aps_exp(pgas_logweight<D>(c, s, i) - M);
+            w8[r] = (e > 0.0) ? (u64)__double2ull_rz(e * scale) : 0ull;
+        }
+    }
+    const int f = tile_find_first_above(w8, s_pref, tau, red, &s_found);
+    if (threadIdx.x == 0 && f >= 0) {
+        int32_t *anc_out = c.anc + (s % c.anc_slabs) * N;
+        anc_out[N - 1] = (int32_t)(tile * APS_TILE + f);
+    }
+}
+
+// final pick over the weights of the final set: rand(pc.rng, pc) (src/container.jl:33-36).
+// One block. If the last decision point resampled, the weights are uniform.
+__global__ void __launch_bounds__(APS_THREADS) k_pick(const __grid_constant__ DevCtx c, const long long plan_idx,
+                                                      const long long step_ctr, const unsigned dom) {
+    __shared__ u64 red[APS_THREADS / 32];
+    __shared__ long long s_tile;
+    __shared__ u64 s_pref;
+    __shared__ int s_found;
+    const long long N = c.N;
+    const StepPlan &p = c.plan[plan_idx];
+    uint64_t w0, w1;
+    aps_philox2x64(0, aps_ctr1((u64)step_ctr, dom, 0), c.sp->key, &w0, &w1);
+    const u64 U = aps_u53(w0);
+    if (p.resampled) {
+        if (threadIdx.x == 0) {
+            const u64 Q = (u64)N << c.S;
+            long long slot = (long long)(floor_uq53(U, Q) >> c.S);
+            if (slot >= N) slot = N - 1;
+            c.st->picked_slot = slot;
+        }
+        return;
+    }
+    const u64 tau = floor_uq53(U, p.Q);
+    const long long nt = c.num_tiles;
+    if (threadIdx.x == 0) s_tile = -1;
+    __syncthreads();
+    for (long long k = threadIdx.x; k < nt; k += APS_THREADS) {
+        const u64 pre = c.tile_prefix[k];
+        const u64 t = c.tile_sum[k];
+        if (pre <= tau && tau < pre + t) {
+            s_tile = k;
+            s_pref = pre;
+        }
+    }
+    __syncthreads();
+    const long long tile = s_tile;
+    if (tile < 0) return;
+    u64 w8[APS_IPT];
+#pragma unroll
+    for (int r = 0; r < APS_IPT; ++r) {
+        const long long i = tile * APS_TILE + (long long)threadIdx.x * APS_IPT + r;
+        w8[r] = i < N ? c.q[i] : 0ull;
+    }
+    const int f = tile_find_first_above(w8, s_pref, tau, red, &s_found);
+    if (threadIdx.x == 0 && f >= 0) c.st->picked_slot = tile * APS_TILE + f;
+}
+
+// trajectory of one final-set slot: T pointer hops through the ancestor store
+__global__ void k_backtrace(const __grid_constant__ DevCtx c, const long long slot_in, double *__restrict__ traj) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const long long N = c.N, T = c.T;
+    const int D = c.d;
+    const long long slot = slot_in >= 0 ? slot_in : c.st->picked_slot;
+    if (slot < 0 || slot >= N) return;
+    long long j = c.anc[(T % c.anc_slabs) * N + slot];
+    for (long long t = T; t >= 1; --t) {
+        const double *xt = c.x + ((t - 1) % c.x_slabs) * (long long)D * N;
+        for (int k = 0; k < D; ++k) traj[(t - 1) * D + k] = xt[(long long)k * N + j];
+        j = c.anc[((t - 1) % c.anc_slabs) * N + j];
+    }
+}
+
+// final particle set as N x d row-major: x_T[anc_{T+1}[i]]   (collect(pc), src/smc.jl:56)
+__global__ void __launch_bounds__(APS_THREADS) k_gather_final(const __grid_constant__ DevCtx c, double *__restrict__ out) {
+    const long long N = c.N, T = c.T;
+    const int D = c.d;
+    const int32_t *anc = c.anc + (T % c.anc_slabs) * N;
+    const double *xt = c.x + ((T - 1) % c.x_slabs) * (long long)D * N;
+    for (long long i = (long long)blockIdx.x * APS_THREADS + threadIdx.x; i < N;
+         i += (long long)gridDim.x * APS_THREADS) {
+        const long long a = anc[i];
+        for (int k = 0; k < D; ++k) out[i * D + k] = xt[(long long)k * N + a];
+    }
+}
+
+// normalised weights W_i = q_i / Q (getweights, src/container.jl:95) or 1/N after a resample
+__global__ void __launch_bounds__(APS_THREADS) k_weights_out(const u64 *__restrict__ q, const StepPlan *p, long long N,
+                                                             int S, int force_uniform, double *__restrict__ out) {
+    const bool uni = force_uniform && p->resampled;
+    const double Qd = uni ? (double)((u64)N << S) : (double)p->Q;
+    const double qu = (double)(1ull << S);
+    for (long long i = (long long)blockIdx.x * APS_THREADS + threadIdx.x; i < N;
+         i += (long long)gridDim.x * APS_THREADS)
+        out[i] = (uni ? qu : (double)q[i]) / Qd;
+}
+
+// int32 0-based -> int64 1-based (operator boundary, Julia Vector{Int})
+__global__ void __launch_bounds__(APS_THREADS) k_to_one_based(const int32_t *__restrict__ in, long long n,
+                                                              long long *__restrict__ out) {
+    for (long long i = (long long)blockIdx.x * APS_THREADS + threadIdx.x; i < n;
+         i += (long long)gridDim.x * APS_THREADS)
+        out[i] = (long long)in[i] + 1;
+}
+
+// synthetic integer weights for aps_bench_resample (hash of the index, roughly log-normal spread)
+__global__ void __launch_bounds__(APS_THREADS) k_bench_weights(u64 *__restrict__ q, long long n, int S, u64 seed) {
+    for (long long i = (long long)blockIdx.x * APS_THREADS + threadIdx.x; i < n;
+         i += (long long)gridDim.x * APS_THREADS) {
+        uint64_t w0, w1;
+        aps_philox2x64((u64)i, 0x42, seed, &w0, &w1);
+        double z0, z1;
+        aps_normal_pair(w0, w1, &z0, &z1);
+        const double e = aps_exp(-0.5 * z0 * z0);
+        q[i] = (u64)__double2ull_rz(e * aps_pow2i(S));
+    }
+}
