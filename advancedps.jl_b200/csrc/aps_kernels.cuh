@@ -78,7 +78,9 @@ template <int D, int OBS>
 __global__ void __launch_bounds__(APS_THREADS) k_propagate(const __grid_constant__ DevCtx c, const long long t) {
     __shared__ u64 red[APS_THREADS / 32];
     const long long N = c.N;
-    const bool reset = c.plan[t - 1].resampled != 0;
+    // log-weights start at zero in every sweep (src/smc.jl:45-51); afterwards they restart from
+    // zero only when the previous decision point resampled (reset_logweights!, container.jl:228)
+    const bool reset = t == 1 || c.plan[t - 1].resampled != 0;
     const int has_ref = c.sp->has_ref;
     const u64 key = c.sp->key;
     double *__restrict__ xt = c.x + ((t - 1) % c.x_slabs) * (long long)D * N;
