@@ -18,7 +18,8 @@ _HDR = [os.path.join(_HERE, "..", "include", f) for f in ("aps_b200.h", "aps_mod
 
 # every symbol include/aps_b200.h declares
 EXPORTS = [
-    "aps_create", "aps_destroy", "aps_set_observations", "aps_sweep", "aps_pick_trajectory",
+    "aps_create", "aps_destroy", "aps_set_observations", "aps_sweep", "aps_sweep_profiled",
+    "aps_pick_trajectory",
     "aps_get_weights", "aps_get_logweights", "aps_get_final_states", "aps_get_trajectory",
     "aps_get_step_stats", "aps_get_states", "aps_get_ancestors", "aps_last_sweep_ms",
     "aps_last_sweep_launches", "aps_resample", "aps_logsumexp", "aps_softmax", "aps_ess",
@@ -114,6 +115,15 @@ class Handle:
             ref = None
         check(lib().aps_sweep(self._h, C.c_uint64(seed), ref, C.byref(le)))
         return le.value
+
+    def sweep_profiled(self, seed):
+        """Unconditional sweep with per-launch CUDA events; returns (logevidence, ms[4], launches[4])
+        for the {propagate, normalise, resample, pgas} kernel classes."""
+        le = C.c_double()
+        ms = (C.c_float * 4)()
+        nl = (C.c_int64 * 4)()
+        check(lib().aps_sweep_profiled(self._h, C.c_uint64(seed), None, C.byref(le), ms, nl))
+        return le.value, list(ms), list(nl)
 
     def pick_trajectory(self, want_traj=True):
         traj = np.zeros((self.T, self.d)) if want_traj else None

@@ -174,6 +174,7 @@ extern "C" int aps_create(const aps_config *cfg, aps_handle **out) {
     DevCtx &c = h->ctx;
     const int d = cfg->model.d;
     c.N = N;
+    c.NS = (N + 31) & ~31LL;
     c.T = T;
     c.d = d;
     c.dy = cfg->model.dy;
@@ -188,10 +189,10 @@ extern "C" int aps_create(const aps_config *cfg, aps_handle **out) {
     c.x_slabs = cfg->keep_history ? T : 2;
     c.anc_slabs = cfg->keep_history ? T + 1 : 2;
     c.num_tiles = (N + APS_TILE - 1) / APS_TILE;
-    CUH(cudaMalloc(&c.x, sizeof(double) * (size_t)c.x_slabs * d * N));
-    CUH(cudaMalloc(&c.anc, sizeof(int32_t) * (size_t)c.anc_slabs * N));
-    CUH(cudaMalloc(&c.logw, sizeof(double) * (size_t)N));
-    CUH(cudaMalloc(&c.q, sizeof(u64) * (size_t)N));
+    CUH(cudaMalloc(&c.x, sizeof(double) * (size_t)c.x_slabs * d * c.NS));
+    CUH(cudaMalloc(&c.anc, sizeof(int32_t) * (size_t)c.anc_slabs * c.NS));
+    CUH(cudaMalloc(&c.logw, sizeof(double) * (size_t)c.NS));
+    CUH(cudaMalloc(&c.q, sizeof(u64) * (size_t)c.NS));
     CUH(cudaMalloc(&c.tile_sum, sizeof(u64) * (size_t)c.num_tiles));
     CUH(cudaMalloc(&c.tile_s1, sizeof(u64) * (size_t)c.num_tiles));
     CUH(cudaMalloc(&c.tile_s2, sizeof(u64) * (size_t)c.num_tiles));
@@ -235,31 +236,59 @@ extern "C" int aps_set_observations(aps_handle *h, const double *Y, int64_t T, i
     return APS_OK;
 }
 
+// optional per-launch CUDA events (aps_sweep_profiled): class 0 propagate, 1 normalise, 2 resample, 3 PGAS
+struct LaunchProf {
+    std::vector<cudaEvent_t> ev;
+    std::vector<int> cls;
+    cudaStream_t st;
+    void begin(int c) {
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        cudaEventRecord(e, st);
+        ev.push_back(e);
+        cls.push_back(c);
+    }
+    void end() {
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        cudaEventRecord(e, st);
+        ev.push_back(e);
+    }
+};
+
 // enqueue every kernel of one sweep on the handle's stream; returns the number of launches
-static long long enqueue_sweep(aps_handle *h) {
+static long long enqueue_sweep(aps_handle *h, LaunchProf *prof = nullptr) {
     const DevCtx &c = h->ctx;
     cudaStream_t st = h->stream;
     long long n = 0;
+#define APS_LAUNCH(cls_, ...)            \
+    do {                                 \
+        if (prof) prof->begin(cls_);     \
+        __VA_ARGS__;                     \
+        if (prof) prof->end();           \
+        ++n;                             \
+    } while (0)
     cudaMemsetAsync(c.acc, 0, sizeof(StepAcc) * (size_t)(c.T + 2), st);
     k_init_sweep<<<1, 32, 0, st>>>(c);
     ++n;
     const int gp = stride_grid(c.N);
     const int gt = (int)c.num_tiles;
+    const int gk1 = (int)(((c.N + 1) / 2 + APS_THREADS - 1) / APS_THREADS);  // one thread per slot pair
     for (long long t = 1; t <= c.T; ++t) {
-        h->f_prop<<<gp, APS_THREADS, 0, st>>>(c, t);
-        k_normalise<IN_LOGW><<<gt, APS_THREADS, 0, st>>>(c, c.logw, t);
-        h->f_res<<<gt, APS_THREADS, 0, st>>>(c, t);
-        n += 3;
+        APS_LAUNCH(0, h->f_prop<<<gk1, APS_THREADS, 0, st>>>(c, t));
+        APS_LAUNCH(1, k_normalise<IN_LOGW><<<gt, APS_THREADS, 0, st>>>(c, c.logw, t));
+        APS_LAUNCH(2, h->f_res<<<gt, APS_THREADS, 0, st>>>(c, t));
         if (c.sampler == APS_PGAS && t >= 2 && t <= c.T - 1) {
-            h->f_pmax<<<gp, APS_THREADS, 0, st>>>(c, t);
-            h->f_psel<<<gt, APS_THREADS, 0, st>>>(c, t);
-            n += 2;
+            APS_LAUNCH(3, h->f_pmax<<<gp, APS_THREADS, 0, st>>>(c, t));
+            APS_LAUNCH(3, h->f_psel<<<gt, APS_THREADS, 0, st>>>(c, t));
         }
     }
+#undef APS_LAUNCH
     return n;
 }
 
-extern "C" int aps_sweep(aps_handle *h, uint64_t master_seed, const double *ref_traj, double *logevidence) {
+static int sweep_impl(aps_handle *h, uint64_t master_seed, const double *ref_traj, double *logevidence,
+                      float *class_ms, int64_t *class_launches) {
     if (!h || !logevidence) return fail(APS_ERR_INVALID, "aps_sweep: null argument");
     if (!h->has_obs) return fail(APS_ERR_INVALID, "aps_sweep: observations not set");
     CU(cudaSetDevice(h->cfg.device));
@@ -280,7 +309,10 @@ extern "C" int aps_sweep(aps_handle *h, uint64_t master_seed, const double *ref_
     h->h_sp->has_ref = has_ref;
     h->h_sp->pad = 0;
     CU(cudaMemcpyAsync(h->d_sp, h->h_sp, sizeof(SweepParams), cudaMemcpyHostToDevice, h->stream));
-    if (!h->graph_ready) {
+    LaunchProf prof;
+    prof.st = h->stream;
+    const bool profiled = class_ms != nullptr;
+    if (!profiled && !h->graph_ready) {
         cudaGraph_t g;
         CU(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
         h->graph_nodes = enqueue_sweep(h);
@@ -290,18 +322,44 @@ extern "C" int aps_sweep(aps_handle *h, uint64_t master_seed, const double *ref_
         h->graph_ready = true;
     }
     CU(cudaEventRecord(h->ev0, h->stream));
-    CU(cudaGraphLaunch(h->graph, h->stream));
+    if (profiled) h->last_launches = enqueue_sweep(h, &prof);
+    else {
+        CU(cudaGraphLaunch(h->graph, h->stream));
+        h->last_launches = h->graph_nodes;
+    }
     CU(cudaEventRecord(h->ev1, h->stream));
     CU(cudaMemcpyAsync(h->h_st, c.st, sizeof(SweepState), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     CU(cudaGetLastError());
     CU(cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1));
-    h->last_launches = h->graph_nodes;
+    if (profiled) {
+        for (int k = 0; k < 4; ++k) {
+            class_ms[k] = 0.f;
+            if (class_launches) class_launches[k] = 0;
+        }
+        for (size_t i = 0; i < prof.cls.size(); ++i) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, prof.ev[2 * i], prof.ev[2 * i + 1]);
+            class_ms[prof.cls[i]] += ms;
+            if (class_launches) class_launches[prof.cls[i]] += 1;
+        }
+        for (cudaEvent_t e : prof.ev) cudaEventDestroy(e);
+    }
     h->swept = true;
     if (h->h_st->err)
         return fail(h->h_st->err, "aps_sweep: particle weights could not be normalised (all -Inf or NaN log-weights)");
     *logevidence = h->h_st->logev;
     return APS_OK;
+}
+
+extern "C" int aps_sweep(aps_handle *h, uint64_t master_seed, const double *ref_traj, double *logevidence) {
+    return sweep_impl(h, master_seed, ref_traj, logevidence, nullptr, nullptr);
+}
+
+extern "C" int aps_sweep_profiled(aps_handle *h, uint64_t master_seed, const double *ref_traj, double *logevidence,
+                                  float *class_ms, int64_t *class_launches) {
+    if (!class_ms) return fail(APS_ERR_INVALID, "aps_sweep_profiled: null class_ms");
+    return sweep_impl(h, master_seed, ref_traj, logevidence, class_ms, class_launches);
 }
 
 #define NEED_SWEEP(name)                                                        \
@@ -404,12 +462,12 @@ extern "C" int aps_get_states(aps_handle *h, int64_t t, double *x_out) {
     const DevCtx &c = h->ctx;
     if (!x_out || t < 1 || t > c.T) return fail(APS_ERR_INVALID, "aps_get_states: t out of range");
     if (!h->cfg.keep_history && t < c.T - 1) return fail(APS_ERR_INVALID, "aps_get_states: history not kept");
-    std::vector<double> soa((size_t)c.N * c.d);
-    CU(cudaMemcpyAsync(soa.data(), c.x + ((t - 1) % c.x_slabs) * (long long)c.d * c.N, sizeof(double) * soa.size(),
+    std::vector<double> soa((size_t)c.NS * c.d);
+    CU(cudaMemcpyAsync(soa.data(), c.x + ((t - 1) % c.x_slabs) * (long long)c.d * c.NS, sizeof(double) * soa.size(),
                        cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     for (long long i = 0; i < c.N; ++i)
-        for (int k = 0; k < c.d; ++k) x_out[i * c.d + k] = soa[(size_t)k * c.N + i];
+        for (int k = 0; k < c.d; ++k) x_out[i * c.d + k] = soa[(size_t)k * c.NS + i];
     return APS_OK;
 }
 
@@ -418,7 +476,7 @@ extern "C" int aps_get_ancestors(aps_handle *h, int64_t t, int32_t *anc_out) {
     const DevCtx &c = h->ctx;
     if (!anc_out || t < 2 || t > c.T + 1) return fail(APS_ERR_INVALID, "aps_get_ancestors: t must be in 2..T+1");
     if (!h->cfg.keep_history && t < c.T) return fail(APS_ERR_INVALID, "aps_get_ancestors: history not kept");
-    CU(cudaMemcpyAsync(anc_out, c.anc + ((t - 1) % c.anc_slabs) * c.N, sizeof(int32_t) * (size_t)c.N,
+    CU(cudaMemcpyAsync(anc_out, c.anc + ((t - 1) % c.anc_slabs) * c.NS, sizeof(int32_t) * (size_t)c.N,
                        cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     return APS_OK;
@@ -507,6 +565,7 @@ static void op_ctx(OpWorkspace &w, DevCtx &c, long long m, long long n_draw) {
     c.sp = w.sp;
     c.anc = w.d_idx32;
     c.N = m;
+    c.NS = m;
     c.T = 0;
     c.x_slabs = 1;
     c.anc_slabs = 1;

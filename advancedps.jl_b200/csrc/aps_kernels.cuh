@@ -35,6 +35,7 @@ struct DevCtx {
     const double *ref;
     const SweepParams *sp;
     long long N, T;
+    long long NS;  // slab stride: N rounded up to a multiple of 32 (aligned vector access)
     long long x_slabs, anc_slabs;
     long long num_tiles;
     int d, dy;
@@ -74,53 +75,75 @@ __global__ void k_init_sweep(const __grid_constant__ DevCtx c) {
 }
 
 // ---------------------------------------------------------------- K1: propagate + reweight
+// One thread per PAIR of adjacent slots (2p, 2p+1): the pair shares D Philox blocks and their
+// Box-Muller normals (aps_pair_normals), ancestors / log-weights / states move as 8- and 16-byte
+// vectors. Block maxima of the new log-weights are folded into one atomicMax per block.
 template <int D, int OBS>
 __global__ void __launch_bounds__(APS_THREADS) k_propagate(const __grid_constant__ DevCtx c, const long long t) {
     __shared__ u64 red[APS_THREADS / 32];
-    const long long N = c.N;
+    const long long N = c.N, NS = c.NS;
     // log-weights start at zero in every sweep (src/smc.jl:45-51); afterwards they restart from
     // zero only when the previous decision point resampled (reset_logweights!, container.jl:228)
     const bool reset = t == 1 || c.plan[t - 1].resampled != 0;
     const int has_ref = c.sp->has_ref;
     const u64 key = c.sp->key;
-    double *__restrict__ xt = c.x + ((t - 1) % c.x_slabs) * (long long)D * N;
-    const double *__restrict__ xp = c.x + ((t + c.x_slabs - 2) % c.x_slabs) * (long long)D * N;
-    const int32_t *__restrict__ anc = c.anc + ((t - 1) % c.anc_slabs) * N;
+    double *__restrict__ xt = c.x + ((t - 1) % c.x_slabs) * (long long)D * NS;
+    const double *__restrict__ xp = c.x + ((t + c.x_slabs - 2) % c.x_slabs) * (long long)D * NS;
+    const int32_t *__restrict__ anc = c.anc + ((t - 1) % c.anc_slabs) * NS;
     double y[APS_MAX_D];
 #pragma unroll
     for (int m = 0; m < APS_MAX_D; ++m) y[m] = m < c.dy ? c.Y[(t - 1) * c.dy + m] : 0.0;
 
     u64 bmax = 0;
     unsigned bad = 0;
-    for (long long i = (long long)blockIdx.x * APS_THREADS + threadIdx.x; i < N;
-         i += (long long)gridDim.x * APS_THREADS) {
-        double x[D];
-        if (has_ref && i == N - 1) {
+    const long long npairs = (N + 1) >> 1;
+    for (long long p = (long long)blockIdx.x * APS_THREADS + threadIdx.x; p < npairs;
+         p += (long long)gridDim.x * APS_THREADS) {
+        double z[2 * D];
+        aps_pair_normals<D>(key, (u64)p, (u64)t, z);
+        const long long i0 = 2 * p;
+        int2 a2 = make_int2(0, 0);
+        if (t > 1) a2 = *reinterpret_cast<const int2 *>(anc + i0);
+        double2 lw2 = make_double2(0.0, 0.0);
+        if (!reset) lw2 = *reinterpret_cast<const double2 *>(c.logw + i0);
+        double xo[2][D];
+        double lwo[2];
 #pragma unroll
-            for (int k = 0; k < D; ++k) x[k] = c.ref[(t - 1) * D + k];
-        } else {
-            double z[D + 1];
-            aps_state_normals<D>(key, (u64)i, (u64)t, z);
-            if (t == 1) {
-                aps_prior_draw<D>(&c.md, z, x);
-            } else {
-                const long long a = anc[i];
-                double xpv[D];
+        for (int h = 0; h < 2; ++h) {
+            const long long i = i0 + h;
+            double x[D];
+            lwo[h] = 0.0;
 #pragma unroll
-                for (int k = 0; k < D; ++k) xpv[k] = xp[(long long)k * N + a];
-                aps_trans_draw<D>(&c.md, xpv, z, x);
+            for (int k = 0; k < D; ++k) x[k] = 0.0;
+            if (i < N) {
+                if (has_ref && i == N - 1) {
+#pragma unroll
+                    for (int k = 0; k < D; ++k) x[k] = c.ref[(t - 1) * D + k];
+                } else if (t == 1) {
+                    aps_prior_draw<D>(&c.md, z + h * D, x);
+                } else {
+                    const long long a = h ? a2.y : a2.x;
+                    double xpv[D];
+#pragma unroll
+                    for (int k = 0; k < D; ++k) xpv[k] = xp[(long long)k * NS + a];
+                    aps_trans_draw<D>(&c.md, xpv, z + h * D, x);
+                }
+                const double ll = aps_obs_logpdf<D, OBS>(&c.md, x, y);
+                const double lw = (reset ? 0.0 : (h ? lw2.y : lw2.x)) + ll;
+                lwo[h] = lw;
+                if (lw != lw) bad = 1;
+                else {
+                    const u64 e = aps_encode_ordered(lw);
+                    bmax = e > bmax ? e : bmax;
+                }
             }
+#pragma unroll
+            for (int k = 0; k < D; ++k) xo[h][k] = x[k];
         }
 #pragma unroll
-        for (int k = 0; k < D; ++k) xt[(long long)k * N + i] = x[k];
-        const double ll = aps_obs_logpdf<D, OBS>(&c.md, x, y);
-        const double lw = (reset ? 0.0 : c.logw[i]) + ll;
-        c.logw[i] = lw;
-        if (lw != lw) bad = 1;
-        else {
-            const u64 e = aps_encode_ordered(lw);
-            bmax = e > bmax ? e : bmax;
-        }
+        for (int k = 0; k < D; ++k)
+            *reinterpret_cast<double2 *>(xt + (long long)k * NS + i0) = make_double2(xo[0][k], xo[1][k]);
+        *reinterpret_cast<double2 *>(c.logw + i0) = make_double2(lwo[0], lwo[1]);
     }
     bmax = block_max_u64(bmax, red);
     bad = __syncthreads_or(bad);
@@ -375,7 +398,7 @@ __global__ void __launch_bounds__(APS_THREADS) k_resample(const __grid_constant_
     __shared__ int wmax[APS_THREADS / 32];
     const long long N = c.N;
     const StepPlan &p = c.plan[s];
-    int32_t *__restrict__ anc_out = c.anc + (s % c.anc_slabs) * N;
+    int32_t *__restrict__ anc_out = c.anc + (s % c.anc_slabs) * c.NS;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const long long base = (long long)blockIdx.x * APS_TILE;
 
@@ -435,7 +458,7 @@ __global__ void __launch_bounds__(APS_THREADS) k_resample(const __grid_constant_
 // lw_i for the PGAS ancestor weights: log f(X_ref[c-1] | X_i[c-2]) + logW_i   (src/pgas.jl:26-46)
 template <int D>
 __device__ __forceinline__ double pgas_logweight(const DevCtx &c, long long s, long long i) {
-    const long long N = c.N;
+    const long long N = c.NS;
     const double *xpp = c.x + ((s - 2) % c.x_slabs) * (long long)D * N;   // states of time s-1 (= c-2)
     const int32_t *anc_cur = c.anc + ((s - 1) % c.anc_slabs) * N;         // ancestors of set s (= c-1)
     const long long a = anc_cur[i];
@@ -576,7 +599,7 @@ __global__ void __launch_bounds__(APS_THREADS) k_pgas_select(const __grid_consta
     }
     const int f = tile_find_first_above(w8, s_pref, tau, red, &s_found);
     if (threadIdx.x == 0 && f >= 0) {
-        int32_t *anc_out = c.anc + (s % c.anc_slabs) * N;
+        int32_t *anc_out = c.anc + (s % c.anc_slabs) * c.NS;
         anc_out[N - 1] = (int32_t)(tile * APS_TILE + f);
     }
 }
@@ -635,11 +658,12 @@ __global__ void k_backtrace(const __grid_constant__ DevCtx c, const long long sl
     const int D = c.d;
     const long long slot = slot_in >= 0 ? slot_in : c.st->picked_slot;
     if (slot < 0 || slot >= N) return;
-    long long j = c.anc[(T % c.anc_slabs) * N + slot];
+    const long long NS = c.NS;
+    long long j = c.anc[(T % c.anc_slabs) * NS + slot];
     for (long long t = T; t >= 1; --t) {
-        const double *xt = c.x + ((t - 1) % c.x_slabs) * (long long)D * N;
-        for (int k = 0; k < D; ++k) traj[(t - 1) * D + k] = xt[(long long)k * N + j];
-        j = c.anc[((t - 1) % c.anc_slabs) * N + j];
+        const double *xt = c.x + ((t - 1) % c.x_slabs) * (long long)D * NS;
+        for (int k = 0; k < D; ++k) traj[(t - 1) * D + k] = xt[(long long)k * NS + j];
+        j = c.anc[((t - 1) % c.anc_slabs) * NS + j];
     }
 }
 
@@ -647,12 +671,12 @@ __global__ void k_backtrace(const __grid_constant__ DevCtx c, const long long sl
 __global__ void __launch_bounds__(APS_THREADS) k_gather_final(const __grid_constant__ DevCtx c, double *__restrict__ out) {
     const long long N = c.N, T = c.T;
     const int D = c.d;
-    const int32_t *anc = c.anc + (T % c.anc_slabs) * N;
-    const double *xt = c.x + ((T - 1) % c.x_slabs) * (long long)D * N;
+    const int32_t *anc = c.anc + (T % c.anc_slabs) * c.NS;
+    const double *xt = c.x + ((T - 1) % c.x_slabs) * (long long)D * c.NS;
     for (long long i = (long long)blockIdx.x * APS_THREADS + threadIdx.x; i < N;
          i += (long long)gridDim.x * APS_THREADS) {
         const long long a = anc[i];
-        for (int k = 0; k < D; ++k) out[i * D + k] = xt[(long long)k * N + a];
+        for (int k = 0; k < D; ++k) out[i * D + k] = xt[(long long)k * c.NS + a];
     }
 }
 

@@ -205,6 +205,8 @@ def _handle_for(tssm, sampler, keep_history=True):
         h._tssm_keepalive = tssm
         _handles.clear()  # keep at most one live handle: particle stores can be tens of GB
         _handles[key] = h
+    else:
+        h.set_observations(tssm.Y)  # the caller may have changed Y in place; T x dy doubles
     return h
 
 

@@ -1,0 +1,302 @@
+#!/usr/bin/env python
+"""Headline benchmark: particle-steps/s of one SMC sweep on BASELINE.json configs[1]
+(linear-Gaussian SSM d=1, T=100, N=1e6, SMC() + resample_systematic), 1..8 GPUs.
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference]
+
+A "step" is one full particle sweep (T+1 resampling rounds, T propagate/reweight rounds) over
+synthetic observations simulated from the model. One JSON line on stdout (rank 0).
+See DESIGN.md section "Measurement" for what each key means.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_PARTICLES = 1_000_000
+T_STEPS = 100
+DATA_KEY = 0xDA7A0002
+MASTER_SEED = 1234
+METRIC = "particle-steps/sec (N*T/s), LGSSM d=1 T=100 N=1e6"
+UNIT = "particle-steps/s"
+WORKLOAD = "configs[1]: linear-Gaussian SSM d=1 T=100 N=1e6 per GPU, SMC() systematic (bare: resample every step)"
+
+
+def env_int(name, default):
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device, self.lines, self.proc = device, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.device)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except (OSError, KeyError, ValueError):
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def make_data():
+    """Synthetic observations simulated from the model. Generated with numpy from the same
+    parameters (no oracle on the product path)."""
+    import numpy as np
+
+    rng = np.random.default_rng(DATA_KEY)
+    x = np.zeros(T_STEPS)
+    y = np.zeros((T_STEPS, 1))
+    a, b, q, h, r = 0.5, 0.2, 0.1, 1.0, 0.1
+    for t in range(T_STEPS):
+        x[t] = rng.normal(0.0, 1.0) if t == 0 else a * x[t - 1] + b + q * rng.normal()
+        y[t, 0] = h * x[t] + r * rng.normal()
+    return y
+
+
+def run_reference(args, rank):
+    """--impl reference: the reference's CPU sweep. The reference itself (Julia) cannot run in this
+    image, so this times the oracle port (oracle/aps_oracle.cpp), single thread -- the reference's
+    sweep is serial (src/container.jl:194,264) -- on a bounded sample of the same workload."""
+    if rank != 0:
+        return
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle as O
+    from advancedps_b200 import _abi, models
+
+    n_sample = env_int("APS_BENCH_REF_N", 200_000)
+    m = models.linear_gaussian()
+    Y = make_data()
+    cfg = _abi.make_config(m, n_sample, T_STEPS)
+    for _ in range(args.warmup):
+        O.sweep(cfg, Y, MASTER_SEED, mode=O.SEQ, history=True)
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        O.sweep(cfg, Y, MASTER_SEED + k, mode=O.SEQ, history=True)
+    dt = time.perf_counter() - t0
+    value = n_sample * T_STEPS * args.steps / dt
+    sample = (f"N={n_sample} of 1e6 particles, full T={T_STEPS}, oracle port in SEQ (reference fp64 order) mode, "
+              f"1 thread of {os.cpu_count()} host cores")
+    out = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(out), flush=True)
+
+
+def cpu_baseline():
+    """Oracle port timed on this box's host cores, rank 0 at N=1 only: one sweep of the sample."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle as O
+    from advancedps_b200 import _abi, models
+
+    n_sample = env_int("APS_BENCH_CPU_N", 1_000_000)
+    cfg = _abi.make_config(models.linear_gaussian(), n_sample, T_STEPS)
+    Y = make_data()
+    t0 = time.perf_counter()
+    O.sweep(cfg, Y, MASTER_SEED, mode=O.SEQ, history=True)
+    dt = time.perf_counter() - t0
+    return {"value": n_sample * T_STEPS / dt, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": f"one full sweep, N={n_sample}, T={T_STEPS} ({dt:.1f} s), oracle port in SEQ mode, single "
+                      f"thread (the reference sweep is serial) of {os.cpu_count()} host cores"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 0)
+
+    rank = env_int("RANK", 0)
+    local_rank = env_int("LOCAL_RANK", 0)
+    world = env_int("WORLD_SIZE", 1)
+
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from advancedps_b200 import _abi, _lib, models, sampler as S
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    model = models.linear_gaussian()
+    Y = make_data()
+    cfg = _abi.make_config(model, N_PARTICLES, T_STEPS, device=local_rank)
+    h = _lib.Handle(cfg)
+    h.set_observations(Y)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+
+    # ---- value: device-resident inputs, CUDA events on the sweep's stream (inside the library)
+    for w in range(args.warmup):
+        h.sweep(MASTER_SEED + rank * 1000 + w)
+    clocks = ClockSampler(local_rank)
+    barrier()
+    clocks.start()
+    dev_ms, launches, logev = 0.0, 0, 0.0
+    wall0 = time.perf_counter()
+    for k in range(args.steps):
+        flush.fill_(k & 0xFF)  # L2 flush between timed iterations (not timed)
+        torch.cuda.synchronize()
+        logev = h.sweep(MASTER_SEED + rank * 1000 + k)
+        dev_ms += h.last_sweep_ms()
+        launches += h.last_sweep_launches()
+    barrier()
+    wall = time.perf_counter() - wall0
+    clk = clocks.stop()
+    t = torch.tensor([dev_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms_max = float(t.item())
+    value = world * N_PARTICLES * T_STEPS * args.steps / (dev_ms_max * 1e-3)
+
+    # ---- e2e: the public API with host buffers; H2D of the observations and D2H of the
+    #      SMCSample fields (weights + log-evidence) inside the timed region
+    tssm = S.TracedSSM(model, Y)
+    smc = S.SMC(N_PARTICLES, S.resample_systematic)
+    rng = np.random.default_rng(MASTER_SEED + rank)
+    del h
+    for _ in range(args.warmup):
+        S.sample(rng, tssm, smc)
+    barrier()
+    e0 = time.perf_counter()
+    for _ in range(args.steps):
+        smp = S.sample(rng, tssm, smc)
+    barrier()
+    e2e_s = time.perf_counter() - e0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * N_PARTICLES * T_STEPS * args.steps / float(t.item())
+    h2d = Y.nbytes + 16
+    d2h = smp.weights.nbytes + 24
+
+    # ---- roofline: per-launch CUDA events around every kernel of one sweep (same workload)
+    hp = S._handle_for(tssm, smc)
+    hp.sweep_profiled(MASTER_SEED)
+    _, cls_ms, cls_n = hp.sweep_profiled(MASTER_SEED)
+    names = ["k_propagate", "k_normalise", "k_resample", "k_pgas"]
+    alg_bytes = {"k_propagate": 28, "k_normalise": 16, "k_resample": 12}  # per particle, DESIGN.md
+    peak, peak_src = measured_peak()
+    tot_ms = sum(cls_ms) or 1.0
+    kern = {}
+    for nm, ms, n in zip(names, cls_ms, cls_n):
+        if n:
+            avg = ms / n
+            gbs = alg_bytes[nm] * N_PARTICLES / (avg * 1e-3) / 1e9 if nm in alg_bytes else None
+            kern[nm] = {"launches": n, "avg_us": 1e3 * avg, "share": ms / tot_ms, "alg_GBps": gbs}
+    dom = max((k for k in kern if k in alg_bytes), key=lambda k: kern[k]["share"])
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": kern[dom]["alg_GBps"], "peak": peak, "unit": "GB/s",
+                "frac": kern[dom]["alg_GBps"] / peak, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": alg_bytes[dom] * N_PARTICLES,
+                "note": "N=1e6 per launch is L2-resident and latency-bound; see resample_isolated for the streaming figure",
+                "kernels": kern}
+    # the graded resample kernel in isolation: 2^25 particles (> L2), L2 flushed between launches
+    n_iso = 1 << 25
+    avg_ms, min_ms = _lib.bench_resample(_abi.RESAMPLE_SYSTEMATIC, n_iso, iters=20, flush_l2=True)
+    iso = 12 * n_iso / (avg_ms * 1e-3) / 1e9
+    roofline["resample_isolated"] = {"n": n_iso, "avg_ms": avg_ms, "min_ms": min_ms, "achieved": iso,
+                                     "frac": iso / peak, "algorithmic_bytes_per_launch": 12 * n_iso,
+                                     "l2": "flushed between launches (512 MB memset)"}
+
+    if rank == 0:
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "n_particles_per_gpu": N_PARTICLES, "n_steps": T_STEPS,
+                       "parallelism": "single GPU" if world == 1 else f"{world} independent replicas (sharded sweep not built yet)",
+                       "l2": "256 MB buffer written between timed sweeps; each sweep also streams 1.2 GB of state/ancestor history",
+                       "timing": "CUDA events on the library's stream around the replayed CUDA graph, max over ranks"},
+            "logevidence": logev, "wall_s": wall,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "api": "sampler.sample(rng, TracedSSM(model, Y), SMC(N, resample_systematic)) -> SMCSample(weights, logevidence)"},
+            "gpu_launches": launches, "clocks": clk, "roofline": roofline,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            out["cpu_baseline"] = cpu_baseline()
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

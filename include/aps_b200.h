@@ -86,6 +86,12 @@ int aps_set_observations(aps_handle *h, const double *Y, int64_t T, int64_t dy);
 #define APS_REF_ON_DEVICE ((const double *)(uintptr_t)1)
 int aps_sweep(aps_handle *h, uint64_t master_seed, const double *ref_traj, double *logevidence);
 
+/* Same sweep, launched kernel by kernel (no CUDA graph) with a CUDA-event pair around every
+ * launch on the handle's stream: class_ms[4] / class_launches[4] receive the summed device time
+ * and launch count of {propagate, normalise, resample, PGAS-select} kernels. Measurement only.  */
+int aps_sweep_profiled(aps_handle *h, uint64_t master_seed, const double *ref_traj, double *logevidence,
+                       float *class_ms, int64_t *class_launches);
+
 /* rand(pc.rng, pc) + trajectory extraction (src/container.jl:33-36, src/smc.jl:127).
  * traj_out: T x d host doubles or NULL; index_out: 0-based slot in the final particle set.      */
 int aps_pick_trajectory(aps_handle *h, double *traj_out, int64_t *index_out);

@@ -67,8 +67,14 @@ APS_HD double aps_sqrt(double x) {
 /* 64x64 -> 128 multiply */
 APS_HD void aps_mul64(uint64_t a, uint64_t b, uint64_t *hi, uint64_t *lo) {
 #if defined(__CUDA_ARCH__)
-    *hi = __umul64hi(a, b);
-    *lo = a * b;
+    /* one pass over the four 32x32 partial products (4 IMAD.WIDE + carries) instead of separate
+     * mul.hi / mul.lo sequences */
+    const uint32_t a0 = (uint32_t)a, a1 = (uint32_t)(a >> 32), b0 = (uint32_t)b, b1 = (uint32_t)(b >> 32);
+    const uint64_t t0 = (uint64_t)a0 * b0;
+    const uint64_t t1 = (uint64_t)a0 * b1 + (t0 >> 32);
+    const uint64_t t2 = (uint64_t)a1 * b0 + (uint32_t)t1;
+    *lo = (t2 << 32) | (uint32_t)t0;
+    *hi = (uint64_t)a1 * b1 + (t1 >> 32) + (t2 >> 32);
 #else
     unsigned __int128 p = (unsigned __int128)a * b;
     *hi = (uint64_t)(p >> 64);
@@ -102,7 +108,8 @@ APS_HD void aps_philox2x64(uint64_t c0, uint64_t c1, uint64_t key, uint64_t *o0,
 
 /* Counter layout used by every draw of a sweep (replaces the per-particle key tree of
  * src/rng.jl:38-42 + src/container.jl:126-159,202-215 by position/time-derived counters):
- *   c0 = global slot index (particle or child), c1 = step << 16 | domain << 8 | block.       */
+ *   c0 = global index (slot pair for state draws, child for resampler draws),
+ *   c1 = step << 16 | domain << 8 | block.                                                    */
 #define APS_DOM_STATE 0u    /* particle state draws (prior / transition)            */
 #define APS_DOM_RESAMPLE 1u /* container stream: resampler uniforms                 */
 #define APS_DOM_PGAS 2u     /* container stream: PGAS ancestor draw                 */

@@ -84,19 +84,18 @@ static inline int aps_model_prepare(const aps_model *m, aps_model_dev *out) {
 /* number of Philox blocks a state draw consumes */
 APS_HD int aps_blocks_for_dim(int d) { return (d + 1) >> 1; }
 
-/* d standard normals for (slot, step) from the sweep key: blocks 0..ceil(d/2)-1 */
+/* State draws are generated per PAIR of adjacent slots p = i >> 1: the pair consumes Philox
+ * blocks j = 0..D-1 at counter (p, ctr1(step, DOM_STATE, j)); their 2D Box-Muller normals, in
+ * block order, go to slot 2p (first D) and slot 2p+1 (last D). No normal is wasted for odd D.  */
 template <int D>
-APS_HD void aps_state_normals(uint64_t key, uint64_t slot, uint64_t step, double *z) {
+APS_HD void aps_pair_normals(uint64_t key, uint64_t pair, uint64_t step, double *z /* 2 D */) {
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-    for (int j = 0; j < (D + 1) / 2; ++j) {
+    for (int j = 0; j < D; ++j) {
         uint64_t w0, w1;
-        aps_philox2x64(slot, aps_ctr1(step, APS_DOM_STATE, (uint32_t)j), key, &w0, &w1);
-        double z0, z1;
-        aps_normal_pair(w0, w1, &z0, &z1);
-        z[2 * j] = z0;
-        if (2 * j + 1 < D) z[2 * j + 1] = z1;
+        aps_philox2x64(pair, aps_ctr1(step, APS_DOM_STATE, (uint32_t)j), key, &w0, &w1);
+        aps_normal_pair(w0, w1, &z[2 * j], &z[2 * j + 1]);
     }
 }
 

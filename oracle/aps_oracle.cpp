@@ -31,7 +31,7 @@
  * Kalman log-likelihoods. RNG bit-streams are NOT pinned to Julia's: the reference draws through
  * Random123.jl / Random.randn / MersenneTwister-based key splitting (src/rng.jl:38-42), none of
  * which is vendored; here every draw is Philox2x64-10 (pinned to Random123's published KATs) at
- * position/time-derived counters, with Box-Muller normals.
+ * position/time-derived counters, with Box-Muller normals (one block per pair of slots).
  */
 #include <stdint.h>
 #include <stdlib.h>
@@ -465,8 +465,9 @@ void advance_all(Sweep &sw, int64_t t) { /* reweight!: src/container.jl:259-302 
         if (hasref && i == N - 1) {
             for (int k = 0; k < D; ++k) x[k] = sw.ref[(size_t)(t - 1) * D + k]; /* pgas.jl:69-72 */
         } else {
-            double z[D + 1];
-            aps_state_normals<D>(sw.key, (uint64_t)i, (uint64_t)t, z);
+            double zz[2 * D];
+            aps_pair_normals<D>(sw.key, (uint64_t)(i >> 1), (uint64_t)t, zz);
+            const double *z = zz + (i & 1) * D;
             if (t == 1) {
                 aps_prior_draw<D>(&sw.md, z, x);
             } else {
