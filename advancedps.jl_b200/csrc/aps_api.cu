@@ -30,8 +30,9 @@ extern "C" const char *aps_last_error(void) { return g_err.c_str(); }
 extern "C" const char *aps_version(void) { return "aps_b200 0.1 (sm_100a)"; }
 
 // ------------------------------------------------------------------ kernel dispatch tables
-typedef void (*prop_fn)(const DevCtx, const long long);
-typedef void (*step_fn)(const DevCtx, const long long);
+typedef void (*prop_fn)(const DevCtx, const long long, double *, const double *, const int32_t *);
+typedef void (*res_fn)(const DevCtx, const long long, int32_t *);
+typedef void (*pgas_fn)(const DevCtx, const long long, const double *, const int32_t *, int32_t *);
 
 template <int OBS>
 static prop_fn prop_for_dim(int d) {
@@ -49,7 +50,7 @@ static prop_fn pick_propagate(int obs, int d) {
         default: return prop_for_dim<APS_OBS_CONST>(d);
     }
 }
-static step_fn pick_pgas_max(int d) {
+static pgas_fn pick_pgas_max(int d) {
     switch (d) {
         case 1: return k_pgas_max<1>;
         case 2: return k_pgas_max<2>;
@@ -57,7 +58,7 @@ static step_fn pick_pgas_max(int d) {
         default: return k_pgas_max<4>;
     }
 }
-static step_fn pick_pgas_select(int d) {
+static pgas_fn pick_pgas_select(int d) {
     switch (d) {
         case 1: return k_pgas_select<1>;
         case 2: return k_pgas_select<2>;
@@ -65,7 +66,7 @@ static step_fn pick_pgas_select(int d) {
         default: return k_pgas_select<4>;
     }
 }
-static step_fn pick_resample(int kind) {
+static res_fn pick_resample(int kind) {
     switch (kind) {
         case APS_RESAMPLE_STRATIFIED: return k_resample<APS_RESAMPLE_STRATIFIED>;
         default: return k_resample<APS_RESAMPLE_SYSTEMATIC>;
@@ -105,7 +106,8 @@ struct aps_handle {
     float last_ms;
     long long last_launches, graph_nodes;
     prop_fn f_prop;
-    step_fn f_res, f_pmax, f_psel;
+    res_fn f_res;
+    pgas_fn f_pmax, f_psel;
 };
 
 static void free_handle(aps_handle *h) {
@@ -274,13 +276,16 @@ static long long enqueue_sweep(aps_handle *h, LaunchProf *prof = nullptr) {
     const int gp = stride_grid(c.N);
     const int gt = (int)c.num_tiles;
     const int gk1 = (int)(((c.N + 1) / 2 + APS_THREADS - 1) / APS_THREADS);  // one thread per slot pair
+    // slab addressing is resolved here, once per launch (no 64-bit modulo in the kernels)
+    auto x_slab = [&](long long t) { return c.x + ((t - 1 + c.x_slabs) % c.x_slabs) * (long long)c.d * c.NS; };
+    auto anc_slab = [&](long long sidx) { return c.anc + ((sidx + c.anc_slabs) % c.anc_slabs) * c.NS; };
     for (long long t = 1; t <= c.T; ++t) {
-        APS_LAUNCH(0, h->f_prop<<<gk1, APS_THREADS, 0, st>>>(c, t));
+        APS_LAUNCH(0, h->f_prop<<<gk1, APS_THREADS, 0, st>>>(c, t, x_slab(t), x_slab(t - 1), anc_slab(t - 1)));
         APS_LAUNCH(1, k_normalise<IN_LOGW><<<gt, APS_THREADS, 0, st>>>(c, c.logw, t));
-        APS_LAUNCH(2, h->f_res<<<gt, APS_THREADS, 0, st>>>(c, t));
+        APS_LAUNCH(2, h->f_res<<<gt, APS_THREADS, 0, st>>>(c, t, anc_slab(t)));
         if (c.sampler == APS_PGAS && t >= 2 && t <= c.T - 1) {
-            APS_LAUNCH(3, h->f_pmax<<<gp, APS_THREADS, 0, st>>>(c, t));
-            APS_LAUNCH(3, h->f_psel<<<gt, APS_THREADS, 0, st>>>(c, t));
+            APS_LAUNCH(3, h->f_pmax<<<gp, APS_THREADS, 0, st>>>(c, t, x_slab(t - 1), anc_slab(t - 1), anc_slab(t)));
+            APS_LAUNCH(3, h->f_psel<<<gt, APS_THREADS, 0, st>>>(c, t, x_slab(t - 1), anc_slab(t - 1), anc_slab(t)));
         }
     }
 #undef APS_LAUNCH
@@ -623,7 +628,7 @@ extern "C" int aps_resample(int kind, const double *wts, int64_t m, int64_t n, u
     rc = op_normalise<IN_W>(w, c, wts, m, key, ctr, &p);
     if (rc) return rc;
     if (p.err) return fail(APS_ERR_WEIGHTS, "sample could not be selected (are the weights normalized?)");
-    pick_resample(kind)<<<(int)c.num_tiles, APS_THREADS, 0, w.stream>>>(c, 0);
+    pick_resample(kind)<<<(int)c.num_tiles, APS_THREADS, 0, w.stream>>>(c, 0, w.d_idx32);
     const bool dev_out = is_device_ptr(idx_out);
     long long *d_out = dev_out ? (long long *)idx_out : w.d_idx64;
     k_to_one_based<<<stride_grid(n), APS_THREADS, 0, w.stream>>>(w.d_idx32, n, d_out);
@@ -754,12 +759,12 @@ extern "C" int aps_bench_resample(int kind, int64_t n, int iters, int flush_l2, 
     cudaEvent_t e0, e1;
     CU(cudaEventCreate(&e0));
     CU(cudaEventCreate(&e1));
-    step_fn f = pick_resample(kind);
+    res_fn f = pick_resample(kind);
     float tot = 0.f, mn = 1e30f;
     for (int it = -3; it < iters; ++it) {  // 3 warm-up launches
         if (flush_l2) CU(cudaMemsetAsync(flush, it & 0xff, flush_bytes, w.stream));
         CU(cudaEventRecord(e0, w.stream));
-        f<<<(int)c.num_tiles, APS_THREADS, 0, w.stream>>>(c, 0);
+        f<<<(int)c.num_tiles, APS_THREADS, 0, w.stream>>>(c, 0, w.d_idx32);
         CU(cudaEventRecord(e1, w.stream));
         CU(cudaStreamSynchronize(w.stream));
         float ms = 0.f;

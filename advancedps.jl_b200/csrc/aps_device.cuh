@@ -17,8 +17,8 @@ typedef unsigned long long u64;
 #define APS_TILE 2048          // particles per tile (normalise + resample kernels)
 #define APS_THREADS 256
 #define APS_IPT 8              // items per thread in a tile
-#define APS_CAP 2304           // children staged per expand pass (9 per thread)
-#define APS_CPT 9
+#define APS_CAP 3072           // children staged per expand pass (12 per thread)
+#define APS_CPT 12
 
 // per-decision-point accumulators, zeroed at sweep start (order-free integer atomics only)
 struct StepAcc {

@@ -79,7 +79,9 @@ __global__ void k_init_sweep(const __grid_constant__ DevCtx c) {
 // Box-Muller normals (aps_pair_normals), ancestors / log-weights / states move as 8- and 16-byte
 // vectors. Block maxima of the new log-weights are folded into one atomicMax per block.
 template <int D, int OBS>
-__global__ void __launch_bounds__(APS_THREADS) k_propagate(const __grid_constant__ DevCtx c, const long long t) {
+__global__ void __launch_bounds__(APS_THREADS) k_propagate(const __grid_constant__ DevCtx c, const long long t,
+                                                           double *__restrict__ xt, const double *__restrict__ xp,
+                                                           const int32_t *__restrict__ anc) {
     __shared__ u64 red[APS_THREADS / 32];
     const long long N = c.N, NS = c.NS;
     // log-weights start at zero in every sweep (src/smc.jl:45-51); afterwards they restart from
@@ -87,12 +89,7 @@ __global__ void __launch_bounds__(APS_THREADS) k_propagate(const __grid_constant
     const bool reset = t == 1 || c.plan[t - 1].resampled != 0;
     const int has_ref = c.sp->has_ref;
     const u64 key = c.sp->key;
-    double *__restrict__ xt = c.x + ((t - 1) % c.x_slabs) * (long long)D * NS;
-    const double *__restrict__ xp = c.x + ((t + c.x_slabs - 2) % c.x_slabs) * (long long)D * NS;
-    const int32_t *__restrict__ anc = c.anc + ((t - 1) % c.anc_slabs) * NS;
-    double y[APS_MAX_D];
-#pragma unroll
-    for (int m = 0; m < APS_MAX_D; ++m) y[m] = m < c.dy ? c.Y[(t - 1) * c.dy + m] : 0.0;
+    const double *__restrict__ y = c.Y + (t - 1) * c.dy;
 
     u64 bmax = 0;
     unsigned bad = 0;
@@ -287,16 +284,16 @@ __device__ __forceinline__ bool thr_le(u64 i, u64 Q, u64 R, u128 Cn) {
     return le_128(add_128_64(mul_64_64(i, Q), R), Cn);
 }
 
-// first i in [0,n] with !(i < n && i Q + R <= C n), starting from a guess k
-__device__ __noinline__ long long first_above_exact(long long k, u64 C, u64 Q, u64 R, long long n) {
+// exact: first i in [0,n] with !(i < n && i Q + R <= C n), starting from a guess k (rare path)
+__device__ __noinline__ int first_above_exact(int k, u64 C, u64 Q, u64 R, int n) {
     const u128 Cn = mul_64_64(C, (u64)n);
     if (k < 0) k = 0;
     if (k > n) k = n;
-    long long lo = k - 2 < 0 ? 0 : k - 2, hi = k + 2 > n ? n : k + 2;
+    int lo = k - 2 < 0 ? 0 : k - 2, hi = k + 2 > n ? n : k + 2;
     if (lo > 0 && !thr_le((u64)(lo - 1), Q, R, Cn)) lo = 0;
     if (hi < n && thr_le((u64)hi, Q, R, Cn)) hi = n;
     while (lo < hi) {
-        const long long mid = (lo + hi) >> 1;
+        const int mid = (int)(((long long)lo + hi) >> 1);
         if (thr_le((u64)mid, Q, R, Cn)) lo = mid + 1;
         else hi = mid;
     }
@@ -305,71 +302,71 @@ __device__ __noinline__ long long first_above_exact(long long k, u64 C, u64 Q, u
 
 #define APS_KEPS 0x1.0p-10
 
-__device__ __forceinline__ long long first_above(double est, u64 C, u64 Q, u64 R, long long n) {
-    // est approximates (C n - R) / Q to ~2^-19 absolute; accept floor(est)+1 unless est is within
-    // APS_KEPS of an integer, in which case the count is settled with exact 128-bit arithmetic.
-    if (est > -4.0e18 && est < 4.0e18) {
-        const double kf = floor(est);
-        const double fr = est - kf;
-        long long k = (long long)kf + 1;
-        if (fr > APS_KEPS && fr < 1.0 - APS_KEPS) return k < 0 ? 0 : (k > n ? n : k);
-        return first_above_exact(k, C, Q, R, n);
-    }
-    return first_above_exact(0, C, Q, R, n);
+// est approximates (C n - R) / Q to ~2^-19 absolute: floor(est)+1 is K unless est lies within
+// APS_KEPS of an integer; those (rare) cases are flagged and settled with exact 128-bit arithmetic.
+__device__ __forceinline__ int first_above_est(double est, int n, bool *unsafe) {
+    const int kf = __double2int_rd(est);
+    const double fr = est - (double)kf;
+    *unsafe = !(fr > APS_KEPS && fr < 1.0 - APS_KEPS);
+    return min(max(kf + 1, 0), n);
 }
 
-template <int KIND>
-__device__ __forceinline__ long long children_below(u64 C, const StepPlan &p, u64 key, u64 s) {
-    if (KIND == APS_RESAMPLE_SYSTEMATIC) {
-        return first_above((double)C * p.ratio - p.roff, C, p.Q, p.R, p.n);
-    } else {  // stratified: child i draws its own offset R_i; only stratum i* = floor(C n / Q) is undecided
-        const long long n = p.n;
-        const long long F = first_above((double)C * p.ratio, C, p.Q, 0ull, n);
-        const u128 Cn = mul_64_64(C, (u64)n);
-        if (F == n && le_128(mul_64_64((u64)n, p.Q), Cn)) return n;
-        const long long istar = F - 1;
-        uint64_t w0, w1;
-        aps_philox2x64((u64)istar, aps_ctr1(s, APS_DOM_RESAMPLE, 0), key, &w0, &w1);
-        const u64 Ri = ceil_uq53(aps_u53(w0), p.Q);
-        return istar + (thr_le((u64)istar, p.Q, Ri, Cn) ? 1 : 0);
-    }
+// stratified: child i draws its own offset R_i; only stratum i* = floor(C n / Q) is undecided.
+// F = first i with i Q > C n (clamped to n).
+__device__ __forceinline__ int strat_children_below(int F, u64 C, u64 Q, int n, u64 key, u64 step) {
+    const u128 Cn = mul_64_64(C, (u64)n);
+    if (F == n && le_128(mul_64_64((u64)n, Q), Cn)) return n;
+    const int istar = F - 1;
+    uint64_t w0, w1;
+    aps_philox2x64((u64)istar, aps_ctr1(step, APS_DOM_RESAMPLE, 0), key, &w0, &w1);
+    const u64 Ri = ceil_uq53(aps_u53(w0), Q);
+    return istar + (thr_le((u64)istar, Q, Ri, Cn) ? 1 : 0);
 }
 
 // Expand phase shared by all resamplers: thread-blocked child ranges [klo_j, khi_j) of the
-// tile's parents -> sorted ancestor indices, staged through shared memory with a max-scan
-// (load-balanced: cost depends on the number of children, not on how skewed the weights are).
-__device__ __forceinline__ void expand_tile(const long long *khi, long long klo0, long long kA, long long kB,
-                                            long long base, int32_t *__restrict__ anc_out, int *own, int *wmax) {
+// tile's parents -> sorted ancestor indices. Parents drop a marker at their first child slot in
+// shared memory; a max-scan (12 consecutive slots per thread, 128-bit shared accesses) turns the
+// markers into parent ids, which leave as 128-bit global stores. Cost follows the number of
+// children, not the skew of the weights.
+__device__ __forceinline__ void expand_tile(const int *khi, int klo0, int kA, int kB, int base,
+                                            int32_t *__restrict__ anc_out, int *own, int *wmax) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (long long cb = kA; cb < kB; cb += APS_CAP) {
-        const int cnt = (int)((kB - cb) < APS_CAP ? (kB - cb) : APS_CAP);
-        for (int p = tid; p < cnt; p += APS_THREADS) own[p] = 0;
+    int4 *own4 = reinterpret_cast<int4 *>(own);
+    for (int cb = kA & ~3; cb < kB; cb += APS_CAP) {
+        const int cnt = (kB - cb) < APS_CAP ? (kB - cb) : APS_CAP;
+        const bool active = tid * APS_CPT < cnt;
+        if (active) {
+            const int4 z = make_int4(0, 0, 0, 0);
+#pragma unroll
+            for (int m = 0; m < APS_CPT / 4; ++m) own4[tid * (APS_CPT / 4) + m] = z;
+        }
         __syncthreads();
-        long long klo = klo0;
+        int klo = klo0;
 #pragma unroll
         for (int j = 0; j < APS_IPT; ++j) {
-            const long long kh = khi[j];
-            if (klo < kh && kh > cb && klo < cb + cnt) {
-                const long long pos = (klo > cb ? klo : cb) - cb;
-                own[pos] = tid * APS_IPT + j + 1;
-            }
+            const int kh = khi[j];
+            const int lo_rel = klo - cb, hi_rel = kh - cb;
+            if (kh > klo && hi_rel > 0 && lo_rel < cnt) own[lo_rel > 0 ? lo_rel : 0] = tid * APS_IPT + j + 1;
             klo = kh;
         }
         __syncthreads();
         int v[APS_CPT];
         int run = 0;
+        if (active) {
 #pragma unroll
-        for (int m = 0; m < APS_CPT; ++m) {
-            const int p = tid * APS_CPT + m;
-            const int o = p < cnt ? own[p] : 0;
-            run = o > run ? o : run;
-            v[m] = run;
+            for (int m = 0; m < APS_CPT / 4; ++m) {
+                const int4 t = own4[tid * (APS_CPT / 4) + m];
+                run = max(run, t.x); v[4 * m] = run;
+                run = max(run, t.y); v[4 * m + 1] = run;
+                run = max(run, t.z); v[4 * m + 2] = run;
+                run = max(run, t.w); v[4 * m + 3] = run;
+            }
         }
         int inc = run;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             const int tt = __shfl_up_sync(0xffffffffu, inc, o);
-            if (lane >= o) inc = tt > inc ? tt : inc;
+            if (lane >= o) inc = max(inc, tt);
         }
         if (lane == 31) wmax[warp] = inc;
         int excl = __shfl_up_sync(0xffffffffu, inc, 1);
@@ -377,32 +374,45 @@ __device__ __forceinline__ void expand_tile(const long long *khi, long long klo0
         __syncthreads();
 #pragma unroll
         for (int w = 0; w < APS_THREADS / 32; ++w)
-            if (w < warp) excl = wmax[w] > excl ? wmax[w] : excl;
+            if (w < warp) excl = max(excl, wmax[w]);
+        if (active) {
+            const int add = base - 1;
 #pragma unroll
-        for (int m = 0; m < APS_CPT; ++m) {
-            const int p = tid * APS_CPT + m;
-            if (p < cnt) own[p] = v[m] > excl ? v[m] : excl;
+            for (int m = 0; m < APS_CPT / 4; ++m) {
+                const int g = cb + tid * APS_CPT + 4 * m;  // global child index of this vector, multiple of 4
+                int4 o;
+                o.x = max(v[4 * m], excl) + add;
+                o.y = max(v[4 * m + 1], excl) + add;
+                o.z = max(v[4 * m + 2], excl) + add;
+                o.w = max(v[4 * m + 3], excl) + add;
+                if (g >= kA && g + 4 <= kB) {
+                    *reinterpret_cast<int4 *>(anc_out + g) = o;
+                } else {
+                    if (g >= kA && g < kB) anc_out[g] = o.x;
+                    if (g + 1 >= kA && g + 1 < kB) anc_out[g + 1] = o.y;
+                    if (g + 2 >= kA && g + 2 < kB) anc_out[g + 2] = o.z;
+                    if (g + 3 >= kA && g + 3 < kB) anc_out[g + 3] = o.w;
+                }
+            }
         }
-        __syncthreads();
-        for (int p = tid; p < cnt; p += APS_THREADS) anc_out[cb + p] = (int32_t)(base + own[p] - 1);
         __syncthreads();
     }
 }
 
 template <int KIND>
-__global__ void __launch_bounds__(APS_THREADS) k_resample(const __grid_constant__ DevCtx c, const long long s) {
+__global__ void __launch_bounds__(APS_THREADS, 4) k_resample(const __grid_constant__ DevCtx c, const long long s,
+                                                             int32_t *__restrict__ anc_out) {
     __shared__ u64 red[APS_THREADS / 32];
-    __shared__ long long wlast[APS_THREADS / 32];
-    __shared__ long long s_k[2];
-    __shared__ int own[APS_CAP];
+    __shared__ int wlast[APS_THREADS / 32];
+    __shared__ int s_k[2];
+    __shared__ __align__(16) int own[APS_CAP];
     __shared__ int wmax[APS_THREADS / 32];
     const long long N = c.N;
-    const StepPlan &p = c.plan[s];
-    int32_t *__restrict__ anc_out = c.anc + (s % c.anc_slabs) * c.NS;
+    const StepPlan *__restrict__ pp = c.plan + s;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const long long base = (long long)blockIdx.x * APS_TILE;
 
-    if (!p.resampled || p.err) {
+    if (!pp->resampled || pp->err) {
         // update_keys! branch (src/container.jl:247): every particle continues, weights kept
 #pragma unroll
         for (int r = 0; r < APS_IPT; ++r) {
@@ -411,6 +421,9 @@ __global__ void __launch_bounds__(APS_THREADS) k_resample(const __grid_constant_
         }
         return;
     }
+    const u64 Q = pp->Q, R = pp->R;
+    const int n = (int)pp->n;
+    const double ratio = pp->ratio, roff = KIND == APS_RESAMPLE_SYSTEMATIC ? pp->roff : 0.0;
 
     // ---- load 8 consecutive integer weights per thread, local inclusive sums
     u64 cum[APS_IPT];
@@ -432,35 +445,54 @@ __global__ void __launch_bounds__(APS_THREADS) k_resample(const __grid_constant_
     u64 tile_total;
     const u64 excl = block_excl_scan_u64(cum[APS_IPT - 1], red, &tile_total) + c.tile_prefix[blockIdx.x];
 
-    // ---- children counts below each inclusive cumulative weight
-    const u64 key = c.sp->key;
-    long long khi[APS_IPT];
+    // ---- children counts below each inclusive cumulative weight (estimate, then rare exact fix-up)
+    int khi[APS_IPT];
+    unsigned unsafe = 0;
 #pragma unroll
-    for (int r = 0; r < APS_IPT; ++r) khi[r] = children_below<KIND>(excl + cum[r], p, key, (u64)(s + c.ctr_offset));
-    long long klo0 = __shfl_up_sync(0xffffffffu, khi[APS_IPT - 1], 1);
-    if (lane == 31) wlast[warp] = khi[APS_IPT - 1];
-    if (tid == 0) {
-        const long long kA = blockIdx.x == 0 ? 0 : children_below<KIND>(excl, p, key, (u64)(s + c.ctr_offset));
-        s_k[0] = kA;
+    for (int r = 0; r < APS_IPT; ++r) {
+        bool u;
+        khi[r] = first_above_est(__fma_rn((double)(excl + cum[r]), ratio, -roff), n, &u);
+        unsafe |= (u ? 1u : 0u) << r;
     }
+    int kA = 0;
+    if (tid == 0 && blockIdx.x != 0) {
+        bool u;
+        kA = first_above_est(__fma_rn((double)excl, ratio, -roff), n, &u);
+        if (u) kA = first_above_exact(kA, excl, Q, KIND == APS_RESAMPLE_SYSTEMATIC ? R : 0ull, n);
+    }
+    if (unsafe) {
+#pragma unroll
+        for (int r = 0; r < APS_IPT; ++r)
+            if ((unsafe >> r) & 1u)
+                khi[r] = first_above_exact(khi[r], excl + cum[r], Q, KIND == APS_RESAMPLE_SYSTEMATIC ? R : 0ull, n);
+    }
+    if (KIND == APS_RESAMPLE_STRATIFIED) {
+        const u64 key = c.sp->key;
+        const u64 step = (u64)(s + c.ctr_offset);
+#pragma unroll
+        for (int r = 0; r < APS_IPT; ++r) khi[r] = strat_children_below(khi[r], excl + cum[r], Q, n, key, step);
+        if (tid == 0 && blockIdx.x != 0) kA = strat_children_below(kA, excl, Q, n, key, step);
+    }
+    int klo0 = __shfl_up_sync(0xffffffffu, khi[APS_IPT - 1], 1);
+    if (lane == 31) wlast[warp] = khi[APS_IPT - 1];
+    if (tid == 0) s_k[0] = kA;
     if (tid == APS_THREADS - 1) s_k[1] = khi[APS_IPT - 1];
     __syncthreads();
     if (lane == 0) klo0 = warp == 0 ? s_k[0] : wlast[warp - 1];
-    const long long kA = s_k[0], kB = s_k[1];
 
-    expand_tile(khi, klo0, kA, kB, base, anc_out, own, wmax);
+    expand_tile(khi, klo0, s_k[0], s_k[1], (int)base, anc_out, own, wmax);
 
     // reference particle keeps the last slot (src/container.jl:219-224); PGAS may overwrite it
-    if (blockIdx.x == gridDim.x - 1 && tid == 0 && p.n < N) anc_out[N - 1] = (int32_t)(N - 1);
+    if (blockIdx.x == gridDim.x - 1 && tid == 0 && n < N) anc_out[N - 1] = (int32_t)(N - 1);
 }
 
 // ---------------------------------------------------------------- categorical draw (PGAS ancestor, final pick)
 // lw_i for the PGAS ancestor weights: log f(X_ref[c-1] | X_i[c-2]) + logW_i   (src/pgas.jl:26-46)
+// xpp: states of time s-1 (= c-2); anc_cur: ancestors of set s (= c-1)
 template <int D>
-__device__ __forceinline__ double pgas_logweight(const DevCtx &c, long long s, long long i) {
+__device__ __forceinline__ double pgas_logweight(const DevCtx &c, long long s, long long i,
+                                                 const double *__restrict__ xpp, const int32_t *__restrict__ anc_cur) {
     const long long N = c.NS;
-    const double *xpp = c.x + ((s - 2) % c.x_slabs) * (long long)D * N;   // states of time s-1 (= c-2)
-    const int32_t *anc_cur = c.anc + ((s - 1) % c.anc_slabs) * N;         // ancestors of set s (= c-1)
     const long long a = anc_cur[i];
     double xp[D], xr[D];
 #pragma unroll
@@ -479,14 +511,16 @@ __device__ __forceinline__ bool pgas_active(const DevCtx &c, long long s) {
 }
 
 template <int D>
-__global__ void __launch_bounds__(APS_THREADS) k_pgas_max(const __grid_constant__ DevCtx c, const long long s) {
+__global__ void __launch_bounds__(APS_THREADS) k_pgas_max(const __grid_constant__ DevCtx c, const long long s,
+                                                          const double *__restrict__ xpp,
+                                                          const int32_t *__restrict__ anc_cur, int32_t *anc_out) {
     __shared__ u64 red[APS_THREADS / 32];
     if (!pgas_active(c, s)) return;
     u64 bmax = 0;
     unsigned bad = 0;
     for (long long i = (long long)blockIdx.x * APS_THREADS + threadIdx.x; i < c.N;
          i += (long long)gridDim.x * APS_THREADS) {
-        const double lw = pgas_logweight<D>(c, s, i);
+        const double lw = pgas_logweight<D>(c, s, i, xpp, anc_cur);
         if (lw != lw) bad = 1;
         else {
             const u64 e = aps_encode_ordered(lw);
@@ -525,7 +559,9 @@ __device__ __forceinline__ int tile_find_first_above(const u64 *w8, u64 prefix, 
 // PGAS: tile totals of the quantised ancestor weights; the last block locates the drawn tile,
 // rescans it and rewires the reference's ancestor pointer (the splice of src/pgas.jl:125-127).
 template <int D>
-__global__ void __launch_bounds__(APS_THREADS) k_pgas_select(const __grid_constant__ DevCtx c, const long long s) {
+__global__ void __launch_bounds__(APS_THREADS) k_pgas_select(const __grid_constant__ DevCtx c, const long long s,
+                                                             const double *__restrict__ xpp,
+                                                             const int32_t *__restrict__ anc_cur, int32_t *anc_out) {
     __shared__ u64 red[APS_THREADS / 32];
     __shared__ unsigned s_last;
     __shared__ long long s_tile;
@@ -542,7 +578,7 @@ __global__ void __launch_bounds__(APS_THREADS) k_pgas_select(const __grid_consta
     for (int r = 0; r < APS_IPT; ++r) {
         const long long i = base + r * APS_THREADS + threadIdx.x;
         if (i < N) {
-            const double e = aps_exp(pgas_logweight<D>(c, s, i) - M);
+            const double e = aps_exp(pgas_logweight<D>(c, s, i, xpp, anc_cur) - M);
             s0 += (e > 0.0) ? (u64)__double2ull_rz(e * scale) : 0ull;
         }
     }
@@ -593,13 +629,12 @@ __global__ void __launch_bounds__(APS_THREADS) k_pgas_select(const __grid_consta
         const long long i = tile * APS_TILE + (long long)threadIdx.x * APS_IPT + r;
         w8[r] = 0;
         if (i < N) {
-            const double e = aps_exp(pgas_logweight<D>(c, s, i) - M);
+            const double e = aps_exp(pgas_logweight<D>(c, s, i, xpp, anc_cur) - M);
             w8[r] = (e > 0.0) ? (u64)__double2ull_rz(e * scale) : 0ull;
         }
     }
     const int f = tile_find_first_above(w8, s_pref, tau, red, &s_found);
     if (threadIdx.x == 0 && f >= 0) {
-        int32_t *anc_out = c.anc + (s % c.anc_slabs) * c.NS;
         anc_out[N - 1] = (int32_t)(tile * APS_TILE + f);
     }
 }
