@@ -12,7 +12,7 @@ import numpy as np
 from . import _abi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libaps_b200.so")
+SO_PATH = os.environ.get("APS_LIB_PATH", os.path.join(_HERE, "libaps_b200.so"))
 _SRC = [os.path.join(_HERE, "csrc", f) for f in ("aps_api.cu", "aps_kernels.cuh", "aps_device.cuh")]
 _HDR = [os.path.join(_HERE, "..", "include", f) for f in ("aps_b200.h", "aps_model.h", "aps_math.h")]
 

@@ -31,23 +31,32 @@ extern "C" const char *aps_version(void) { return "aps_b200 0.1 (sm_100a)"; }
 
 // ------------------------------------------------------------------ kernel dispatch tables
 typedef void (*prop_fn)(const DevCtx, const long long, double *, const double *, const int32_t *);
-typedef void (*res_fn)(const DevCtx, const long long, int32_t *);
+typedef void (*res_fn)(const DevCtx, const long long, int32_t *, const CUtensorMap);
 typedef void (*pgas_fn)(const DevCtx, const long long, const double *, const int32_t *, int32_t *);
 
-template <int OBS>
-static prop_fn prop_for_dim(int d) {
-    switch (d) {
-        case 1: return k_propagate<1, OBS>;
-        case 2: return k_propagate<2, OBS>;
-        case 3: return k_propagate<3, OBS>;
-        default: return k_propagate<4, OBS>;
+template <int D, int OBS>
+static prop_fn prop_for_dy(int dy) {
+    switch (dy) {
+        case 1: return k_propagate<D, 1, OBS>;
+        case 2: return k_propagate<D, 2, OBS>;
+        case 3: return k_propagate<D, 3, OBS>;
+        default: return k_propagate<D, 4, OBS>;
     }
 }
-static prop_fn pick_propagate(int obs, int d) {
+template <int OBS>
+static prop_fn prop_for_dim(int d, int dy) {
+    switch (d) {
+        case 1: return prop_for_dy<1, OBS>(dy);
+        case 2: return prop_for_dy<2, OBS>(dy);
+        case 3: return prop_for_dy<3, OBS>(dy);
+        default: return prop_for_dy<4, OBS>(dy);
+    }
+}
+static prop_fn pick_propagate(int obs, int d, int dy) {
     switch (obs) {
-        case APS_OBS_LINEAR_GAUSS: return prop_for_dim<APS_OBS_LINEAR_GAUSS>(d);
-        case APS_OBS_STOCH_VOL: return prop_for_dim<APS_OBS_STOCH_VOL>(d);
-        default: return prop_for_dim<APS_OBS_CONST>(d);
+        case APS_OBS_LINEAR_GAUSS: return prop_for_dim<APS_OBS_LINEAR_GAUSS>(d, dy);
+        case APS_OBS_STOCH_VOL: return prop_for_dim<APS_OBS_STOCH_VOL>(d, 1);
+        default: return prop_for_dim<APS_OBS_CONST>(d, 1);
     }
 }
 static pgas_fn pick_pgas_max(int d) {
@@ -73,6 +82,55 @@ static res_fn pick_resample(int kind) {
     }
 }
 
+// ------------------------------------------------------------------ TMA descriptor of the integer-weight array
+// q viewed as [rows][APS_IPT] u64 (128-byte rows); box = APS_THREADS rows; 128-byte swizzle.
+typedef CUresult (*encode_tiled_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                    const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static int make_q_tensormap(CUtensorMap *out, u64 *q, long long n_padded) {
+    static encode_tiled_fn enc = nullptr;
+    if (!enc) {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+        if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn)
+            return fail(APS_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+        enc = (encode_tiled_fn)fn;
+    }
+    const cuuint64_t rows = (cuuint64_t)((n_padded + APS_IPT - 1) / APS_IPT);
+    const cuuint64_t gdim[2] = {APS_IPT, rows};
+    const cuuint64_t gstride[1] = {APS_IPT * 8};
+    const cuuint32_t box[2] = {APS_IPT, APS_THREADS};
+    const cuuint32_t estride[2] = {1, 1};
+    CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_UINT64, 2, q, gdim, gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(APS_ERR_CUDA, "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
+    return APS_OK;
+}
+template <typename F>
+static void prefer_max_smem(F f) {
+    // every kernel of a step asks for the same shared-memory carve-out, so the SMs never have to
+    // drain to re-partition L1 / shared memory between consecutive launches
+    cudaFuncSetAttribute(f, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+}
+static int enable_k3_smem() {
+    static bool done = false;
+    if (done) return APS_OK;
+    prefer_max_smem(k_resample<APS_RESAMPLE_SYSTEMATIC>);
+    prefer_max_smem(k_resample<APS_RESAMPLE_STRATIFIED>);
+    prefer_max_smem(k_normalise<IN_LOGW>);
+    prefer_max_smem(k_normalise<IN_W>);
+    prefer_max_smem(k_normalise<IN_Q>);
+    prefer_max_smem(k_bench_weights);
+    prefer_max_smem(k_to_one_based);
+    prefer_max_smem(k_vector_max<IN_W>);
+    prefer_max_smem(k_vector_max<IN_LOGW>);
+    CU(cudaFuncSetAttribute(k_resample<APS_RESAMPLE_SYSTEMATIC>, cudaFuncAttributeMaxDynamicSharedMemorySize, APS_K3_DYN_SMEM));
+    CU(cudaFuncSetAttribute(k_resample<APS_RESAMPLE_STRATIFIED>, cudaFuncAttributeMaxDynamicSharedMemorySize, APS_K3_DYN_SMEM));
+    done = true;
+    return APS_OK;
+}
+
 static int g_sm_count = 0;
 static int sm_count() {
     if (g_sm_count == 0) {
@@ -85,7 +143,7 @@ static int sm_count() {
 }
 // grid for the grid-stride kernels: a multiple of the SM count, 8 resident CTAs of 256 per SM
 static int stride_grid(long long n) {
-    long long need = (n + APS_THREADS - 1) / APS_THREADS;
+    long long need = (n + APS_K1_THREADS - 1) / APS_K1_THREADS;
     long long cap = (long long)sm_count() * 8;
     if (need < 1) need = 1;
     return (int)(need < cap ? need : cap);
@@ -105,6 +163,7 @@ struct aps_handle {
     bool graph_ready, has_obs, swept, ref_valid;
     float last_ms;
     long long last_launches, graph_nodes;
+    CUtensorMap tmap_q;
     prop_fn f_prop;
     res_fn f_res;
     pgas_fn f_pmax, f_psel;
@@ -210,13 +269,21 @@ extern "C" int aps_create(const aps_config *cfg, aps_handle **out) {
     CUH(cudaMallocHost(&h->h_sp, sizeof(SweepParams)));
     CUH(cudaMallocHost(&h->h_st, sizeof(SweepState)));
     CUH(cudaMemset(c.plan, 0, sizeof(StepPlan) * (size_t)(T + 2)));
+    CUH(cudaMemset(c.q, 0, sizeof(u64) * (size_t)c.NS));  // the padding past N must read as zero weight
+    if (make_q_tensormap(&h->tmap_q, c.q, c.NS) || enable_k3_smem()) {
+        free_handle(h);
+        return APS_ERR_CUDA;
+    }
     c.Y = h->d_Y;
     c.ref = h->d_ref;
     c.sp = h->d_sp;
-    h->f_prop = pick_propagate(cfg->model.obs_kind, d);
+    h->f_prop = pick_propagate(cfg->model.obs_kind, d, cfg->model.dy);
+    prefer_max_smem(h->f_prop);
     h->f_res = pick_resample(cfg->resampler);
     h->f_pmax = pick_pgas_max(d);
     h->f_psel = pick_pgas_select(d);
+    prefer_max_smem(h->f_pmax);
+    prefer_max_smem(h->f_psel);
 #undef CUH
     *out = h;
     return APS_OK;
@@ -275,16 +342,19 @@ static long long enqueue_sweep(aps_handle *h, LaunchProf *prof = nullptr) {
     ++n;
     const int gp = stride_grid(c.N);
     const int gt = (int)c.num_tiles;
-    const int gk1 = (int)(((c.N + 1) / 2 + APS_THREADS - 1) / APS_THREADS);  // one thread per slot pair
+    // one thread per slot pair, grid-stride over at most 5 resident blocks per SM
+    long long gk1l = ((c.N + 1) / 2 + APS_K1_THREADS - 1) / APS_K1_THREADS;
+    if (gk1l > (long long)sm_count() * 5) gk1l = (long long)sm_count() * 5;
+    const int gk1 = (int)gk1l;
     // slab addressing is resolved here, once per launch (no 64-bit modulo in the kernels)
     auto x_slab = [&](long long t) { return c.x + ((t - 1 + c.x_slabs) % c.x_slabs) * (long long)c.d * c.NS; };
     auto anc_slab = [&](long long sidx) { return c.anc + ((sidx + c.anc_slabs) % c.anc_slabs) * c.NS; };
     for (long long t = 1; t <= c.T; ++t) {
-        APS_LAUNCH(0, h->f_prop<<<gk1, APS_THREADS, 0, st>>>(c, t, x_slab(t), x_slab(t - 1), anc_slab(t - 1)));
+        APS_LAUNCH(0, h->f_prop<<<gk1, APS_K1_THREADS, 0, st>>>(c, t, x_slab(t), x_slab(t - 1), anc_slab(t - 1)));
         APS_LAUNCH(1, k_normalise<IN_LOGW><<<gt, APS_THREADS, 0, st>>>(c, c.logw, t));
-        APS_LAUNCH(2, h->f_res<<<gt, APS_THREADS, 0, st>>>(c, t, anc_slab(t)));
+        APS_LAUNCH(2, h->f_res<<<gt, APS_THREADS, APS_K3_DYN_SMEM, st>>>(c, t, anc_slab(t), h->tmap_q));
         if (c.sampler == APS_PGAS && t >= 2 && t <= c.T - 1) {
-            APS_LAUNCH(3, h->f_pmax<<<gp, APS_THREADS, 0, st>>>(c, t, x_slab(t - 1), anc_slab(t - 1), anc_slab(t)));
+            APS_LAUNCH(3, h->f_pmax<<<gp, APS_K1_THREADS, 0, st>>>(c, t, x_slab(t - 1), anc_slab(t - 1), anc_slab(t)));
             APS_LAUNCH(3, h->f_psel<<<gt, APS_THREADS, 0, st>>>(c, t, x_slab(t - 1), anc_slab(t - 1), anc_slab(t)));
         }
     }
@@ -505,6 +575,7 @@ struct OpWorkspace {
     std::mutex mu;
     cudaStream_t stream = nullptr;
     long long cap_m = 0, cap_n = 0;
+    CUtensorMap tmap_q;
     double *d_in = nullptr, *d_wout = nullptr;
     u64 *d_q = nullptr, *tile_sum = nullptr, *tile_s1 = nullptr, *tile_s2 = nullptr, *tile_prefix = nullptr;
     int32_t *d_idx32 = nullptr;
@@ -531,7 +602,7 @@ static int ws_reserve(OpWorkspace &w, long long m, long long n) {
         const long long nt = (m + APS_TILE - 1) / APS_TILE;
         CU(cudaMalloc(&w.d_in, sizeof(double) * (size_t)m));
         CU(cudaMalloc(&w.d_wout, sizeof(double) * (size_t)m));
-        CU(cudaMalloc(&w.d_q, sizeof(u64) * (size_t)m));
+        CU(cudaMalloc(&w.d_q, sizeof(u64) * (size_t)(m + 32)));
         CU(cudaMalloc(&w.tile_sum, sizeof(u64) * (size_t)nt));
         CU(cudaMalloc(&w.tile_s1, sizeof(u64) * (size_t)nt));
         CU(cudaMalloc(&w.tile_s2, sizeof(u64) * (size_t)nt));
@@ -570,7 +641,7 @@ static void op_ctx(OpWorkspace &w, DevCtx &c, long long m, long long n_draw) {
     c.sp = w.sp;
     c.anc = w.d_idx32;
     c.N = m;
-    c.NS = m;
+    c.NS = (m + 31) & ~31LL;
     c.T = 0;
     c.x_slabs = 1;
     c.anc_slabs = 1;
@@ -600,7 +671,8 @@ static int op_normalise(OpWorkspace &w, DevCtx &c, const double *in, long long m
     sp.pad = 0;
     CU(cudaMemcpyAsync(w.sp, &sp, sizeof(sp), cudaMemcpyHostToDevice, w.stream));
     CU(cudaMemsetAsync(w.acc, 0, sizeof(StepAcc), w.stream));
-    k_vector_max<INPUT><<<stride_grid(m), APS_THREADS, 0, w.stream>>>(d_in, m, w.acc);
+    if (c.NS > m) CU(cudaMemsetAsync(w.d_q + m, 0, sizeof(u64) * (size_t)(c.NS - m), w.stream));  // zero-weight padding
+    k_vector_max<INPUT><<<stride_grid(m), APS_K1_THREADS, 0, w.stream>>>(d_in, m, w.acc);
     c.ctr_offset = (long long)ctr;
     k_normalise<INPUT><<<(int)c.num_tiles, APS_THREADS, 0, w.stream>>>(c, d_in, 0);
     CU(cudaMemcpyAsync(plan_host, w.plan, sizeof(StepPlan), cudaMemcpyDeviceToHost, w.stream));
@@ -628,7 +700,11 @@ extern "C" int aps_resample(int kind, const double *wts, int64_t m, int64_t n, u
     rc = op_normalise<IN_W>(w, c, wts, m, key, ctr, &p);
     if (rc) return rc;
     if (p.err) return fail(APS_ERR_WEIGHTS, "sample could not be selected (are the weights normalized?)");
-    pick_resample(kind)<<<(int)c.num_tiles, APS_THREADS, 0, w.stream>>>(c, 0, w.d_idx32);
+    rc = make_q_tensormap(&w.tmap_q, w.d_q, c.NS);
+    if (rc) return rc;
+    rc = enable_k3_smem();
+    if (rc) return rc;
+    pick_resample(kind)<<<(int)c.num_tiles, APS_THREADS, APS_K3_DYN_SMEM, w.stream>>>(c, 0, w.d_idx32, w.tmap_q);
     const bool dev_out = is_device_ptr(idx_out);
     long long *d_out = dev_out ? (long long *)idx_out : w.d_idx64;
     k_to_one_based<<<stride_grid(n), APS_THREADS, 0, w.stream>>>(w.d_idx32, n, d_out);
@@ -746,6 +822,7 @@ extern "C" int aps_bench_resample(int kind, int64_t n, int iters, int flush_l2, 
     sp.pad = 0;
     CU(cudaMemcpyAsync(w.sp, &sp, sizeof(sp), cudaMemcpyHostToDevice, w.stream));
     CU(cudaMemsetAsync(w.acc, 0, sizeof(StepAcc), w.stream));
+    if (c.NS > n) CU(cudaMemsetAsync(w.d_q + n, 0, sizeof(u64) * (size_t)(c.NS - n), w.stream));
     k_bench_weights<<<stride_grid(n), APS_THREADS, 0, w.stream>>>(w.d_q, n, c.S, seed);
     k_normalise<IN_Q><<<(int)c.num_tiles, APS_THREADS, 0, w.stream>>>(c, nullptr, 0);
     StepPlan p;
@@ -760,11 +837,15 @@ extern "C" int aps_bench_resample(int kind, int64_t n, int iters, int flush_l2, 
     CU(cudaEventCreate(&e0));
     CU(cudaEventCreate(&e1));
     res_fn f = pick_resample(kind);
+    rc = make_q_tensormap(&w.tmap_q, w.d_q, c.NS);
+    if (rc) return rc;
+    rc = enable_k3_smem();
+    if (rc) return rc;
     float tot = 0.f, mn = 1e30f;
     for (int it = -3; it < iters; ++it) {  // 3 warm-up launches
         if (flush_l2) CU(cudaMemsetAsync(flush, it & 0xff, flush_bytes, w.stream));
         CU(cudaEventRecord(e0, w.stream));
-        f<<<(int)c.num_tiles, APS_THREADS, 0, w.stream>>>(c, 0, w.d_idx32);
+        f<<<(int)c.num_tiles, APS_THREADS, APS_K3_DYN_SMEM, w.stream>>>(c, 0, w.d_idx32, w.tmap_q);
         CU(cudaEventRecord(e1, w.stream));
         CU(cudaStreamSynchronize(w.stream));
         float ms = 0.f;

@@ -8,17 +8,20 @@
 //   tile_sum / tile_prefix [tile]  u64   per-2048-particle tile totals and their exclusive scan
 //   plan   [s]                     per-decision-point scalars (max, total, logZ, ESS, decision, thresholds)
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "aps_b200.h"
 
 typedef unsigned long long u64;
 
-#define APS_TILE 2048          // particles per tile (normalise + resample kernels)
-#define APS_THREADS 256
-#define APS_IPT 8              // items per thread in a tile
-#define APS_CAP 3072           // children staged per expand pass (12 per thread)
-#define APS_CPT 12
+#define APS_THREADS 128         // threads per block of the tile kernels (normalise, resample, select)
+#define APS_IPT 16              // items per thread in a tile: 16 u64 = one 128-byte row of the TMA box
+#define APS_TILE (APS_THREADS * APS_IPT)   // 2048 particles per tile
+#define APS_CPT 20              // child slots per thread in one expand pass
+#define APS_CAP (APS_THREADS * APS_CPT)    // 2560 children staged per pass
+#define APS_WARPS (APS_THREADS / 32)
+#define APS_K1_THREADS 256      // threads per block of the grid-stride kernels (propagate, maxima)
 
 // per-decision-point accumulators, zeroed at sweep start (order-free integer atomics only)
 struct StepAcc {
@@ -37,11 +40,13 @@ struct StepPlan {
     double ess;      // effective sample size (src/container.jl:116-119)
     u64 Q;           // integer weight total
     u64 R;           // ceil(U Q / 2^53): systematic offset in integer weight units
-    double ratio;    // n / Q   (estimate only; results are verified exactly)
-    double roff;     // R / Q
+    double ratio;    // 2^20 n / Q   (estimate only; results are verified exactly)
+    double roff;     // 2^20 R / Q
     long long n;     // children to draw (N, or N-1 with a reference particle)
     int resampled;   // decision of resample_propagate! (src/container.jl:233-251)
     int err;         // aps_status if the weights could not be normalised
+    int guard;       // half-width (units of 2^-20) of the band around integers where est is not trusted
+    int pad;
 };
 
 struct SweepState {
@@ -76,46 +81,54 @@ __device__ __forceinline__ u64 warp_max_u64(u64 v) {
     return v;
 }
 
-// block-wide sum for APS_THREADS threads; result valid in every thread. smem: >= 8 u64
+// block-wide reductions / scan for NW warps (NW a power of two <= 8); results valid in every
+// thread. smem: >= NW u64. The NW warp partials are combined with NW-lane shuffle steps.
+template <int NW>
 __device__ __forceinline__ u64 block_sum_u64(u64 v, u64 *smem) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     v = warp_sum_u64(v);
     __syncthreads();
     if (lane == 0) smem[warp] = v;
     __syncthreads();
-    u64 t = 0;
+    u64 t = smem[lane & (NW - 1)];
 #pragma unroll
-    for (int w = 0; w < APS_THREADS / 32; ++w) t += smem[w];
+    for (int o = NW / 2; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
     return t;
 }
 
+template <int NW>
 __device__ __forceinline__ u64 block_max_u64(u64 v, u64 *smem) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     v = warp_max_u64(v);
     __syncthreads();
     if (lane == 0) smem[warp] = v;
     __syncthreads();
-    u64 t = 0;
+    u64 t = smem[lane & (NW - 1)];
 #pragma unroll
-    for (int w = 0; w < APS_THREADS / 32; ++w) t = smem[w] > t ? smem[w] : t;
+    for (int o = NW / 2; o > 0; o >>= 1) {
+        const u64 x = __shfl_xor_sync(0xffffffffu, t, o);
+        t = x > t ? x : t;
+    }
     return t;
 }
 
-// block-wide exclusive scan of one u64 per thread; *total gets the block sum. smem: >= 8 u64
+// block-wide exclusive scan of one u64 per thread; *total gets the block sum
+template <int NW>
 __device__ __forceinline__ u64 block_excl_scan_u64(u64 v, u64 *smem, u64 *total) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    u64 inc = warp_incl_scan_u64(v, lane);
+    const u64 inc = warp_incl_scan_u64(v, lane);
     __syncthreads();
     if (lane == 31) smem[warp] = inc;
     __syncthreads();
-    u64 off = 0, tot = 0;
+    u64 w = smem[lane & (NW - 1)];
 #pragma unroll
-    for (int w = 0; w < APS_THREADS / 32; ++w) {
-        u64 s = smem[w];
-        if (w < warp) off += s;
-        tot += s;
+    for (int o = 1; o < NW; o <<= 1) {
+        const u64 t = __shfl_up_sync(0xffffffffu, w, o, NW);
+        if ((lane & (NW - 1)) >= o) w += t;
     }
-    *total = tot;
+    *total = __shfl_sync(0xffffffffu, w, NW - 1, NW);
+    u64 off = __shfl_sync(0xffffffffu, w, (warp + NW - 1) & (NW - 1), NW);
+    if (warp == 0) off = 0;
     return off + inc - v;
 }
 
@@ -146,4 +159,39 @@ __device__ __forceinline__ u64 ceil_uq53(u64 U, u64 Q) {
 __device__ __forceinline__ u64 floor_uq53(u64 U, u64 Q) {
     u128 p = mul_64_64(U, Q);
     return (p.hi << 11) | (p.lo >> 53);
+}
+
+// ---------------------------------------------------------------- TMA (cp.async.bulk.tensor) + mbarrier
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "APS_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra APS_DONE;\n"
+        "bra APS_WAIT;\n"
+        "APS_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// 2-D tiled bulk tensor load global -> shared, completion signalled on an mbarrier (SASS: UTMALDG)
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, uint64_t *bar, int x, int y) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+            smem_u32(dst)),
+        "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y)
+        : "memory");
+}
+// L2 prefetch of a tile that a later block will load (keeps HBM busy across block boundaries)
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap *map, int x, int y) {
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(map), "r"(x), "r"(y) : "memory");
 }

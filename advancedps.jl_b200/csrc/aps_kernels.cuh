@@ -67,6 +67,8 @@ __global__ void k_init_sweep(const __grid_constant__ DevCtx c) {
         p.n = c.N - (c.sp->has_ref ? 1 : 0);
         p.resampled = c.bare ? 1 : ((double)c.N <= c.ess_threshold * (double)c.N ? 1 : 0);
         p.err = 0;
+        p.guard = 8;
+        p.pad = 0;
         c.plan[0] = p;
         c.st->logev = 0.0;
         c.st->err = 0;
@@ -78,11 +80,11 @@ __global__ void k_init_sweep(const __grid_constant__ DevCtx c) {
 // One thread per PAIR of adjacent slots (2p, 2p+1): the pair shares D Philox blocks and their
 // Box-Muller normals (aps_pair_normals), ancestors / log-weights / states move as 8- and 16-byte
 // vectors. Block maxima of the new log-weights are folded into one atomicMax per block.
-template <int D, int OBS>
-__global__ void __launch_bounds__(APS_THREADS) k_propagate(const __grid_constant__ DevCtx c, const long long t,
+template <int D, int DY, int OBS>
+__global__ void __launch_bounds__(APS_K1_THREADS) k_propagate(const __grid_constant__ DevCtx c, const long long t,
                                                            double *__restrict__ xt, const double *__restrict__ xp,
                                                            const int32_t *__restrict__ anc) {
-    __shared__ u64 red[APS_THREADS / 32];
+    __shared__ u64 red[APS_K1_THREADS / 32];
     const long long N = c.N, NS = c.NS;
     // log-weights start at zero in every sweep (src/smc.jl:45-51); afterwards they restart from
     // zero only when the previous decision point resampled (reset_logweights!, container.jl:228)
@@ -94,8 +96,8 @@ __global__ void __launch_bounds__(APS_THREADS) k_propagate(const __grid_constant
     u64 bmax = 0;
     unsigned bad = 0;
     const long long npairs = (N + 1) >> 1;
-    for (long long p = (long long)blockIdx.x * APS_THREADS + threadIdx.x; p < npairs;
-         p += (long long)gridDim.x * APS_THREADS) {
+    for (long long p = (long long)blockIdx.x * APS_K1_THREADS + threadIdx.x; p < npairs;
+         p += (long long)gridDim.x * APS_K1_THREADS) {
         double z[2 * D];
         aps_pair_normals<D>(key, (u64)p, (u64)t, z);
         const long long i0 = 2 * p;
@@ -125,7 +127,7 @@ __global__ void __launch_bounds__(APS_THREADS) k_propagate(const __grid_constant
                     for (int k = 0; k < D; ++k) xpv[k] = xp[(long long)k * NS + a];
                     aps_trans_draw<D>(&c.md, xpv, z + h * D, x);
                 }
-                const double ll = aps_obs_logpdf<D, OBS>(&c.md, x, y);
+                const double ll = aps_obs_logpdf<D, DY, OBS>(&c.md, x, y);
                 const double lw = (reset ? 0.0 : (h ? lw2.y : lw2.x)) + ll;
                 lwo[h] = lw;
                 if (lw != lw) bad = 1;
@@ -142,7 +144,7 @@ __global__ void __launch_bounds__(APS_THREADS) k_propagate(const __grid_constant
             *reinterpret_cast<double2 *>(xt + (long long)k * NS + i0) = make_double2(xo[0][k], xo[1][k]);
         *reinterpret_cast<double2 *>(c.logw + i0) = make_double2(lwo[0], lwo[1]);
     }
-    bmax = block_max_u64(bmax, red);
+    bmax = block_max_u64<APS_K1_THREADS / 32>(bmax, red);
     bad = __syncthreads_or(bad);
     if (threadIdx.x == 0) {
         if (bmax) atomicMax(&c.acc[t].max_enc, bmax);
@@ -152,12 +154,12 @@ __global__ void __launch_bounds__(APS_THREADS) k_propagate(const __grid_constant
 
 // max of a plain vector (operator-level entry points)
 template <int INPUT>
-__global__ void __launch_bounds__(APS_THREADS) k_vector_max(const double *__restrict__ in, long long n, StepAcc *acc) {
-    __shared__ u64 red[APS_THREADS / 32];
+__global__ void __launch_bounds__(APS_K1_THREADS) k_vector_max(const double *__restrict__ in, long long n, StepAcc *acc) {
+    __shared__ u64 red[APS_K1_THREADS / 32];
     u64 bmax = 0;
     unsigned bad = 0;
-    for (long long i = (long long)blockIdx.x * APS_THREADS + threadIdx.x; i < n;
-         i += (long long)gridDim.x * APS_THREADS) {
+    for (long long i = (long long)blockIdx.x * APS_K1_THREADS + threadIdx.x; i < n;
+         i += (long long)gridDim.x * APS_K1_THREADS) {
         const double v = in[i];
         if (v != v || (INPUT == IN_W && v < 0.0)) bad = 1;
         else {
@@ -165,7 +167,7 @@ __global__ void __launch_bounds__(APS_THREADS) k_vector_max(const double *__rest
             bmax = e > bmax ? e : bmax;
         }
     }
-    bmax = block_max_u64(bmax, red);
+    bmax = block_max_u64<APS_K1_THREADS / 32>(bmax, red);
     bad = __syncthreads_or(bad);
     if (threadIdx.x == 0) {
         if (bmax) atomicMax(&acc->max_enc, bmax);
@@ -208,9 +210,9 @@ __global__ void __launch_bounds__(APS_THREADS) k_normalise(const __grid_constant
             s2 += qs * qs;
         }
     }
-    s0 = block_sum_u64(s0, red);
-    s1 = block_sum_u64(s1, red);
-    s2 = block_sum_u64(s2, red);
+    s0 = block_sum_u64<APS_WARPS>(s0, red);
+    s1 = block_sum_u64<APS_WARPS>(s1, red);
+    s2 = block_sum_u64<APS_WARPS>(s2, red);
     if (threadIdx.x == 0) {
         c.tile_sum[blockIdx.x] = s0;
         c.tile_s1[blockIdx.x] = s1;
@@ -235,13 +237,13 @@ __global__ void __launch_bounds__(APS_THREADS) k_normalise(const __grid_constant
         a2 += __ldcg(&c.tile_s2[k]);
     }
     u64 Q;
-    u64 run = block_excl_scan_u64(a0, red, &Q);
+    u64 run = block_excl_scan_u64<APS_WARPS>(a0, red, &Q);
     for (long long k = lo; k < hi; ++k) {
         c.tile_prefix[k] = run;
         run += __ldcg(&c.tile_sum[k]);
     }
-    const u64 Q1 = block_sum_u64(a1, red);
-    const u64 Q2 = block_sum_u64(a2, red);
+    const u64 Q1 = block_sum_u64<APS_WARPS>(a1, red);
+    const u64 Q2 = block_sum_u64<APS_WARPS>(a2, red);
     if (threadIdx.x == 0) {
         StepPlan p;
         int err = 0;
@@ -262,9 +264,11 @@ __global__ void __launch_bounds__(APS_THREADS) k_normalise(const __grid_constant
         uint64_t w0, w1;
         aps_philox2x64(0, aps_ctr1((u64)(s + c.ctr_offset), APS_DOM_RESAMPLE, 0), c.sp->key, &w0, &w1);
         p.R = ceil_uq53(aps_u53(w0), Q);
-        p.ratio = (double)p.n / (double)Q;
-        p.roff = (double)p.R / (double)Q;
+        p.ratio = 0x1.0p24 * ((double)p.n / (double)Q);
+        p.roff = 0x1.0p24 * ((double)p.R / (double)Q);
         p.err = err;
+        p.guard = 2 + (int)((p.n + (1LL << 25) - 1) >> 25);
+        p.pad = 0;
         if (c.st) {
             if (err) c.st->err = err;
             else if (s >= 1) {
@@ -300,15 +304,19 @@ __device__ __noinline__ int first_above_exact(int k, u64 C, u64 Q, u64 R, int n)
     return lo;
 }
 
-#define APS_KEPS 0x1.0p-10
-
-// est approximates (C n - R) / Q to ~2^-19 absolute: floor(est)+1 is K unless est lies within
-// APS_KEPS of an integer; those (rare) cases are flagged and settled with exact 128-bit arithmetic.
-__device__ __forceinline__ int first_above_est(double est, int n, bool *unsafe) {
-    const int kf = __double2int_rd(est);
-    const double fr = est - (double)kf;
-    *unsafe = !(fr > APS_KEPS && fr < 1.0 - APS_KEPS);
-    return min(max(kf + 1, 0), n);
+// est approximates 2^24 (C n - R) / Q. Error budget: (double)C, (double)Q, the division, the
+// 2^24 scaling (exact) and the fma each contribute <= 2^-53 relative on a value <= 2^24 n, and the
+// floor to 2^-24 units one more unit, so the true value is within (1 + n 2^-26.5) units of the
+// integer v below. floor(est)+1 is therefore K unless the 24-bit fraction lies within
+// guard = 2 + ceil(n / 2^25) units of an integer; those cases are flagged (*unsafe is OR-ed) and
+// settled with exact 128-bit arithmetic (about 5e-7 of all evaluations at n = 2^20).
+#define APS_KFRAC_BITS 24
+__device__ __forceinline__ int first_above_est(double est20, int n, int guard, bool *unsafe) {
+    const long long v = __double2ll_rd(est20);
+    const int kf = (int)(v >> APS_KFRAC_BITS);
+    const unsigned fr = (unsigned)v & ((1u << APS_KFRAC_BITS) - 1u);
+    *unsafe = *unsafe || (fr - (unsigned)guard >= (1u << APS_KFRAC_BITS) - 2u * (unsigned)guard);
+    return min(kf + 1, n);
 }
 
 // stratified: child i draws its own offset R_i; only stratum i* = floor(C n / Q) is undecided.
@@ -323,26 +331,89 @@ __device__ __forceinline__ int strat_children_below(int F, u64 C, u64 Q, int n, 
     return istar + (thr_le((u64)istar, Q, Ri, Cn) ? 1 : 0);
 }
 
-// Expand phase shared by all resamplers: thread-blocked child ranges [klo_j, khi_j) of the
-// tile's parents -> sorted ancestor indices. Parents drop a marker at their first child slot in
-// shared memory; a max-scan (12 consecutive slots per thread, 128-bit shared accesses) turns the
-// markers into parent ids, which leave as 128-bit global stores. Cost follows the number of
-// children, not the skew of the weights.
-__device__ __forceinline__ void expand_tile(const int *khi, int klo0, int kA, int kB, int base,
-                                            int32_t *__restrict__ anc_out, int *own, int *wmax) {
+// Expand phase shared by all resamplers. Parents drop a marker (their tile-local id) at their
+// first child slot in shared memory; a max-scan (20 consecutive slots per thread, 128-bit shared
+// accesses) turns the markers into parent ids, which leave as 128-bit global stores. Cost follows
+// the number of children, not the skew of the weights.
+//
+// scan + store for the child slots [cb, cb + cnt) whose markers are already in own[]
+__device__ __forceinline__ void expand_scan_store(int cb, int cnt, int kA, int kB, int base,
+                                                  int32_t *__restrict__ anc_out, int *own, int *wmax) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int4 *own4 = reinterpret_cast<const int4 *>(own);
+    const bool active = tid * APS_CPT < cnt;
+    int v[APS_CPT];
+    int run = 0;
+    if (active) {
+#pragma unroll
+        for (int m = 0; m < APS_CPT / 4; ++m) {
+            const int4 t = own4[tid * (APS_CPT / 4) + m];
+            run = max(run, t.x); v[4 * m] = run;
+            run = max(run, t.y); v[4 * m + 1] = run;
+            run = max(run, t.z); v[4 * m + 2] = run;
+            run = max(run, t.w); v[4 * m + 3] = run;
+        }
+    }
+    int inc = run;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int tt = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc = max(inc, tt);
+    }
+    if (lane == 31) wmax[warp] = inc;
+    int excl = __shfl_up_sync(0xffffffffu, inc, 1);
+    if (lane == 0) excl = 0;
+    __syncthreads();
+    {
+        int w = wmax[lane & (APS_WARPS - 1)];
+#pragma unroll
+        for (int o = 1; o < APS_WARPS; o <<= 1) {
+            const int tt = __shfl_up_sync(0xffffffffu, w, o, APS_WARPS);
+            if ((lane & (APS_WARPS - 1)) >= o) w = max(w, tt);
+        }
+        const int prev = __shfl_sync(0xffffffffu, w, (warp + APS_WARPS - 1) & (APS_WARPS - 1), APS_WARPS);
+        if (warp > 0) excl = max(excl, prev);
+    }
+    if (active) {
+        const int add = base - 1;
+#pragma unroll
+        for (int m = 0; m < APS_CPT / 4; ++m) {
+            const int g = cb + tid * APS_CPT + 4 * m;  // global child index of this vector, multiple of 4
+            int4 o;
+            o.x = max(v[4 * m], excl) + add;
+            o.y = max(v[4 * m + 1], excl) + add;
+            o.z = max(v[4 * m + 2], excl) + add;
+            o.w = max(v[4 * m + 3], excl) + add;
+            if (g >= kA && g + 4 <= kB) {
+                *reinterpret_cast<int4 *>(anc_out + g) = o;
+            } else {
+                if (g >= kA && g < kB) anc_out[g] = o.x;
+                if (g + 1 >= kA && g + 1 < kB) anc_out[g + 1] = o.y;
+                if (g + 2 >= kA && g + 2 < kB) anc_out[g + 2] = o.z;
+                if (g + 3 >= kA && g + 3 < kB) anc_out[g + 3] = o.w;
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ void zero_own(int *own) {
     int4 *own4 = reinterpret_cast<int4 *>(own);
+    const int4 z = make_int4(0, 0, 0, 0);
+#pragma unroll
+    for (int m = 0; m < APS_CPT / 4; ++m) own4[threadIdx.x * (APS_CPT / 4) + m] = z;
+}
+
+// general (rare) path: any number of children, clipped chunk by chunk. khi: inclusive child
+// counts of this thread's parents, klo0: count below its first parent.
+__device__ __noinline__ void expand_tile_general(const int *khi, int klo0, int kA, int kB, int base,
+                                                 int32_t *__restrict__ anc_out, int *own, int *wmax) {
+    const int tid = threadIdx.x;
     for (int cb = kA & ~3; cb < kB; cb += APS_CAP) {
         const int cnt = (kB - cb) < APS_CAP ? (kB - cb) : APS_CAP;
-        const bool active = tid * APS_CPT < cnt;
-        if (active) {
-            const int4 z = make_int4(0, 0, 0, 0);
-#pragma unroll
-            for (int m = 0; m < APS_CPT / 4; ++m) own4[tid * (APS_CPT / 4) + m] = z;
-        }
+        __syncthreads();
+        zero_own(own);
         __syncthreads();
         int klo = klo0;
-#pragma unroll
         for (int j = 0; j < APS_IPT; ++j) {
             const int kh = khi[j];
             const int lo_rel = klo - cb, hi_rel = kh - cb;
@@ -350,66 +421,53 @@ __device__ __forceinline__ void expand_tile(const int *khi, int klo0, int kA, in
             klo = kh;
         }
         __syncthreads();
-        int v[APS_CPT];
-        int run = 0;
-        if (active) {
-#pragma unroll
-            for (int m = 0; m < APS_CPT / 4; ++m) {
-                const int4 t = own4[tid * (APS_CPT / 4) + m];
-                run = max(run, t.x); v[4 * m] = run;
-                run = max(run, t.y); v[4 * m + 1] = run;
-                run = max(run, t.z); v[4 * m + 2] = run;
-                run = max(run, t.w); v[4 * m + 3] = run;
-            }
-        }
-        int inc = run;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int tt = __shfl_up_sync(0xffffffffu, inc, o);
-            if (lane >= o) inc = max(inc, tt);
-        }
-        if (lane == 31) wmax[warp] = inc;
-        int excl = __shfl_up_sync(0xffffffffu, inc, 1);
-        if (lane == 0) excl = 0;
-        __syncthreads();
-#pragma unroll
-        for (int w = 0; w < APS_THREADS / 32; ++w)
-            if (w < warp) excl = max(excl, wmax[w]);
-        if (active) {
-            const int add = base - 1;
-#pragma unroll
-            for (int m = 0; m < APS_CPT / 4; ++m) {
-                const int g = cb + tid * APS_CPT + 4 * m;  // global child index of this vector, multiple of 4
-                int4 o;
-                o.x = max(v[4 * m], excl) + add;
-                o.y = max(v[4 * m + 1], excl) + add;
-                o.z = max(v[4 * m + 2], excl) + add;
-                o.w = max(v[4 * m + 3], excl) + add;
-                if (g >= kA && g + 4 <= kB) {
-                    *reinterpret_cast<int4 *>(anc_out + g) = o;
-                } else {
-                    if (g >= kA && g < kB) anc_out[g] = o.x;
-                    if (g + 1 >= kA && g + 1 < kB) anc_out[g + 1] = o.y;
-                    if (g + 2 >= kA && g + 2 < kB) anc_out[g + 2] = o.z;
-                    if (g + 3 >= kA && g + 3 < kB) anc_out[g + 3] = o.w;
-                }
-            }
-        }
-        __syncthreads();
+        expand_scan_store(cb, cnt, kA, kB, base, anc_out, own, wmax);
     }
 }
 
+// estimate with an immediate exact fix-up when it cannot be trusted (retry path of a tile)
 template <int KIND>
-__global__ void __launch_bounds__(APS_THREADS, 4) k_resample(const __grid_constant__ DevCtx c, const long long s,
-                                                             int32_t *__restrict__ anc_out) {
+__device__ __forceinline__ int children_below_checked(u64 C, u64 Q, u64 R, int n, double ratio, double roff, int guard,
+                                                      u64 key, u64 step) {
+    bool u = false;
+    int k = first_above_est(__fma_rn((double)C, ratio, -roff), n, guard, &u);
+    if (u) k = first_above_exact(k, C, Q, KIND == APS_RESAMPLE_SYSTEMATIC ? R : 0ull, n);
+    if (KIND == APS_RESAMPLE_STRATIFIED) k = strat_children_below(k, C, Q, n, key, step);
+    return k;
+}
+
+// children below cumulative weight C from the estimate; *unsafe is OR-ed when it cannot be trusted
+template <int KIND>
+__device__ __forceinline__ int children_below_fast(u64 C, u64 Q, int n, double ratio, double roff, int guard,
+                                                   u64 key, u64 step, bool *unsafe) {
+    int k = first_above_est(__fma_rn((double)C, ratio, -roff), n, guard, unsafe);
+    if (KIND == APS_RESAMPLE_STRATIFIED) k = strat_children_below(k, C, Q, n, key, step);
+    return k;
+}
+
+// One tile of APS_TILE parents per block: reads their integer weights (8 B each), writes the
+// sorted ancestor indices of the children they own (4 B each).
+//
+// The tile's weights arrive through one TMA bulk-tensor copy: q is described to the TMA unit as a
+// [rows][16] u64 tensor (128-byte rows), the box is 256 rows, and the 128-byte hardware swizzle
+// (16-byte chunk index XOR row & 7) makes the thread-blocked read-back -- thread t owns row t,
+// i.e. 16 consecutive weights -- free of bank conflicts. Rows past the end of the tensor are
+// zero-filled by the hardware, so ragged tails need no special case.
+#define APS_TILE_BYTES (APS_TILE * 8)
+#define APS_K3_DYN_SMEM (APS_TILE_BYTES + APS_CAP * 4)
+template <int KIND>
+__global__ void __launch_bounds__(APS_THREADS, 8) k_resample(const __grid_constant__ DevCtx c, const long long s,
+                                                             int32_t *__restrict__ anc_out,
+                                                             const __grid_constant__ CUtensorMap tmap_q) {
+    extern __shared__ __align__(1024) unsigned char dynsmem[];  // [tile: APS_TILE u64, swizzled][own: APS_CAP int]
     __shared__ u64 red[APS_THREADS / 32];
-    __shared__ int wlast[APS_THREADS / 32];
-    __shared__ int s_k[2];
-    __shared__ __align__(16) int own[APS_CAP];
     __shared__ int wmax[APS_THREADS / 32];
+    __shared__ __align__(8) uint64_t mbar;
+    unsigned char *tilebuf = dynsmem;
+    int *own = reinterpret_cast<int *>(dynsmem + APS_TILE_BYTES);
     const long long N = c.N;
     const StepPlan *__restrict__ pp = c.plan + s;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x;
     const long long base = (long long)blockIdx.x * APS_TILE;
 
     if (!pp->resampled || pp->err) {
@@ -421,66 +479,90 @@ __global__ void __launch_bounds__(APS_THREADS, 4) k_resample(const __grid_consta
         }
         return;
     }
+    if (tid == 0) {
+        if (smem_u32(tilebuf) & 1023u) __trap();  // the 128-byte swizzle pattern assumes a 1 KB aligned tile
+        mbar_init(&mbar, 1);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        mbar_expect_tx(&mbar, APS_TILE_BYTES);
+        tma_load_2d(tilebuf, &tmap_q, &mbar, 0, (int)(base / APS_IPT));
+        // pull the tile that a block ~2 residency waves later will need from HBM into L2 now
+        const long long pf = (long long)blockIdx.x + 2LL * 8 * 148;
+        if (pf < (long long)gridDim.x) tma_prefetch_2d(&tmap_q, 0, (int)(pf * APS_THREADS));
+    }
     const u64 Q = pp->Q, R = pp->R;
     const int n = (int)pp->n;
+    const int guard = pp->guard;
     const double ratio = pp->ratio, roff = KIND == APS_RESAMPLE_SYSTEMATIC ? pp->roff : 0.0;
+    const u64 key = KIND == APS_RESAMPLE_STRATIFIED ? c.sp->key : 0ull;
+    const u64 step = (u64)(s + c.ctr_offset);
+    const u64 tprefix = c.tile_prefix[blockIdx.x];
 
-    // ---- load 8 consecutive integer weights per thread, local inclusive sums
+    zero_own(own);
+    if (tid < 32) mbar_wait(&mbar, 0);  // one warp polls the mbarrier, the others park on the block barrier
+    __syncthreads();
+
+    // ---- this thread's 16 consecutive integer weights (row tid of the swizzled tile), local inclusive sums
     u64 cum[APS_IPT];
-    const long long i0 = base + (long long)tid * APS_IPT;
-    if (base + APS_TILE <= N) {
-        const ulonglong2 *src = reinterpret_cast<const ulonglong2 *>(c.q + i0);
+    {
+        const unsigned char *row = tilebuf + tid * (APS_IPT * 8);
 #pragma unroll
         for (int r = 0; r < APS_IPT / 2; ++r) {
-            const ulonglong2 v = __ldg(src + r);
+            const ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(row + ((r ^ (tid & 7)) << 4));
             cum[2 * r] = v.x;
             cum[2 * r + 1] = v.y;
         }
-    } else {
-#pragma unroll
-        for (int r = 0; r < APS_IPT; ++r) cum[r] = (i0 + r < N) ? c.q[i0 + r] : 0ull;
     }
 #pragma unroll
     for (int r = 1; r < APS_IPT; ++r) cum[r] += cum[r - 1];
     u64 tile_total;
-    const u64 excl = block_excl_scan_u64(cum[APS_IPT - 1], red, &tile_total) + c.tile_prefix[blockIdx.x];
+    const u64 excl = block_excl_scan_u64<APS_WARPS>(cum[APS_IPT - 1], red, &tile_total) + tprefix;  // syncs: own[] is zeroed
 
-    // ---- children counts below each inclusive cumulative weight (estimate, then rare exact fix-up)
-    int khi[APS_IPT];
-    unsigned unsafe = 0;
-#pragma unroll
-    for (int r = 0; r < APS_IPT; ++r) {
-        bool u;
-        khi[r] = first_above_est(__fma_rn((double)(excl + cum[r]), ratio, -roff), n, &u);
-        unsafe |= (u ? 1u : 0u) << r;
-    }
-    int kA = 0;
-    if (tid == 0 && blockIdx.x != 0) {
-        bool u;
-        kA = first_above_est(__fma_rn((double)excl, ratio, -roff), n, &u);
-        if (u) kA = first_above_exact(kA, excl, Q, KIND == APS_RESAMPLE_SYSTEMATIC ? R : 0ull, n);
-    }
-    if (unsafe) {
-#pragma unroll
-        for (int r = 0; r < APS_IPT; ++r)
-            if ((unsafe >> r) & 1u)
-                khi[r] = first_above_exact(khi[r], excl + cum[r], Q, KIND == APS_RESAMPLE_SYSTEMATIC ? R : 0ull, n);
-    }
-    if (KIND == APS_RESAMPLE_STRATIFIED) {
-        const u64 key = c.sp->key;
-        const u64 step = (u64)(s + c.ctr_offset);
-#pragma unroll
-        for (int r = 0; r < APS_IPT; ++r) khi[r] = strat_children_below(khi[r], excl + cum[r], Q, n, key, step);
-        if (tid == 0 && blockIdx.x != 0) kA = strat_children_below(kA, excl, Q, n, key, step);
-    }
-    int klo0 = __shfl_up_sync(0xffffffffu, khi[APS_IPT - 1], 1);
-    if (lane == 31) wlast[warp] = khi[APS_IPT - 1];
-    if (tid == 0) s_k[0] = kA;
-    if (tid == APS_THREADS - 1) s_k[1] = khi[APS_IPT - 1];
-    __syncthreads();
-    if (lane == 0) klo0 = warp == 0 ? s_k[0] : wlast[warp - 1];
+    // ---- child range of the tile and of this thread (every thread evaluates the three bounds itself)
+    bool unsafe = false;
+    const int kA = blockIdx.x == 0 ? 0 : children_below_fast<KIND>(tprefix, Q, n, ratio, roff, guard, key, step, &unsafe);
+    const int kB = children_below_fast<KIND>(tprefix + tile_total, Q, n, ratio, roff, guard, key, step, &unsafe);
+    int klo = tid == 0 ? kA : children_below_fast<KIND>(excl, Q, n, ratio, roff, guard, key, step, &unsafe);
+    const int cb = kA & ~3;
+    const bool single = kB - cb <= APS_CAP;
 
-    expand_tile(khi, klo0, s_k[0], s_k[1], (int)base, anc_out, own, wmax);
+    // ---- fast path: estimate the children below each parent and drop its marker at once
+    if (single) {
+#pragma unroll
+        for (int r = 0; r < APS_IPT; ++r) {
+            const int k = children_below_fast<KIND>(excl + cum[r], Q, n, ratio, roff, guard, key, step, &unsafe);
+            if (k > klo) own[klo - cb] = tid * APS_IPT + r + 1;
+            klo = k;
+        }
+    }
+    const int slow = __syncthreads_or((unsafe || !single) ? 1 : 0);
+    if (!slow) {
+        expand_scan_store(cb, kB - cb, kA, kB, (int)base, anc_out, own, wmax);
+    } else {
+        // ---- retry (some estimate fell within the guard band of an integer, or the tile owns
+        //      more children than one pass holds): same walk with exact fix-ups where needed
+        const int kAx = blockIdx.x == 0 ? 0 : children_below_checked<KIND>(tprefix, Q, R, n, ratio, roff, guard, key, step);
+        const int kBx = children_below_checked<KIND>(tprefix + tile_total, Q, R, n, ratio, roff, guard, key, step);
+        int klx = tid == 0 ? kAx : children_below_checked<KIND>(excl, Q, R, n, ratio, roff, guard, key, step);
+        const int cbx = kAx & ~3;
+        if (kBx - cbx <= APS_CAP) {
+            zero_own(own);  // every thread is past the marker loop (the __syncthreads_or above)
+            __syncthreads();
+            for (int r = 0; r < APS_IPT; ++r) {
+                const int k = children_below_checked<KIND>(excl + cum[r], Q, R, n, ratio, roff, guard, key, step);
+                if (k > klx) own[klx - cbx] = tid * APS_IPT + r + 1;
+                klx = k;
+            }
+            __syncthreads();
+            expand_scan_store(cbx, kBx - cbx, kAx, kBx, (int)base, anc_out, own, wmax);
+        } else {
+            int khi[APS_IPT];
+            for (int r = 0; r < APS_IPT; ++r)
+                khi[r] = children_below_checked<KIND>(excl + cum[r], Q, R, n, ratio, roff, guard, key, step);
+            expand_tile_general(khi, klx, kAx, kBx, (int)base, anc_out, own, wmax);
+        }
+    }
 
     // reference particle keeps the last slot (src/container.jl:219-224); PGAS may overwrite it
     if (blockIdx.x == gridDim.x - 1 && tid == 0 && n < N) anc_out[N - 1] = (int32_t)(N - 1);
@@ -511,15 +593,15 @@ __device__ __forceinline__ bool pgas_active(const DevCtx &c, long long s) {
 }
 
 template <int D>
-__global__ void __launch_bounds__(APS_THREADS) k_pgas_max(const __grid_constant__ DevCtx c, const long long s,
+__global__ void __launch_bounds__(APS_K1_THREADS) k_pgas_max(const __grid_constant__ DevCtx c, const long long s,
                                                           const double *__restrict__ xpp,
                                                           const int32_t *__restrict__ anc_cur, int32_t *anc_out) {
-    __shared__ u64 red[APS_THREADS / 32];
+    __shared__ u64 red[APS_K1_THREADS / 32];
     if (!pgas_active(c, s)) return;
     u64 bmax = 0;
     unsigned bad = 0;
-    for (long long i = (long long)blockIdx.x * APS_THREADS + threadIdx.x; i < c.N;
-         i += (long long)gridDim.x * APS_THREADS) {
+    for (long long i = (long long)blockIdx.x * APS_K1_THREADS + threadIdx.x; i < c.N;
+         i += (long long)gridDim.x * APS_K1_THREADS) {
         const double lw = pgas_logweight<D>(c, s, i, xpp, anc_cur);
         if (lw != lw) bad = 1;
         else {
@@ -527,7 +609,7 @@ __global__ void __launch_bounds__(APS_THREADS) k_pgas_max(const __grid_constant_
             bmax = e > bmax ? e : bmax;
         }
     }
-    bmax = block_max_u64(bmax, red);
+    bmax = block_max_u64<APS_K1_THREADS / 32>(bmax, red);
     bad = __syncthreads_or(bad);
     if (threadIdx.x == 0) {
         if (bmax) atomicMax(&c.acc[s].sel_max_enc, bmax);
@@ -543,7 +625,7 @@ __device__ __forceinline__ int tile_find_first_above(const u64 *w8, u64 prefix, 
 #pragma unroll
     for (int r = 1; r < APS_IPT; ++r) cum[r] = cum[r - 1] + w8[r];
     u64 tot;
-    const u64 excl = block_excl_scan_u64(cum[APS_IPT - 1], red, &tot) + prefix;
+    const u64 excl = block_excl_scan_u64<APS_WARPS>(cum[APS_IPT - 1], red, &tot) + prefix;
     if (threadIdx.x == 0) *s_found = 0x7fffffff;
     __syncthreads();
     int mine = 0x7fffffff;
@@ -582,7 +664,7 @@ __global__ void __launch_bounds__(APS_THREADS) k_pgas_select(const __grid_consta
             s0 += (e > 0.0) ? (u64)__double2ull_rz(e * scale) : 0ull;
         }
     }
-    s0 = block_sum_u64(s0, red);
+    s0 = block_sum_u64<APS_WARPS>(s0, red);
     // tile_s1 is free at this point of the step (the plan of s is already written)
     if (threadIdx.x == 0) {
         c.tile_s1[blockIdx.x] = s0;
@@ -600,7 +682,7 @@ __global__ void __launch_bounds__(APS_THREADS) k_pgas_select(const __grid_consta
     u64 a0 = 0;
     for (long long k = lo; k < hi; ++k) a0 += __ldcg(&c.tile_s1[k]);
     u64 Qs;
-    u64 run = block_excl_scan_u64(a0, red, &Qs);
+    u64 run = block_excl_scan_u64<APS_WARPS>(a0, red, &Qs);
     if (threadIdx.x == 0) {
         s_tile = -1;
         uint64_t w0, w1;

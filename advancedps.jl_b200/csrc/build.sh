@@ -6,4 +6,4 @@ cd "$(dirname "$0")"
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 $NVCC -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -fmad=false \
   -Xcompiler -fPIC,-ffp-contract=off,-mfma -Xptxas -v \
-  -I../../include -shared -o ../libaps_b200.so aps_api.cu -lcudart "$@"
+  -I../../include -shared -o ${APS_OUT:-../libaps_b200.so} aps_api.cu -lcudart "$@"

@@ -151,8 +151,8 @@ APS_HD double aps_trans_logpdf(const aps_model_dev *md, const double *xp, const 
     return acc;
 }
 
-/* log g(y | x)   (src/pgas.jl:74-76: logdensity(obs, step, x, y)); y has dy entries */
-template <int D, int OBS>
+/* log g(y | x)   (src/pgas.jl:74-76: logdensity(obs, step, x, y)); y has DY entries */
+template <int D, int DY, int OBS>
 APS_HD double aps_obs_logpdf(const aps_model_dev *md, const double *x, const double *y) {
     if (OBS == APS_OBS_CONST) return y[0];
     if (OBS == APS_OBS_STOCH_VOL) {
@@ -162,8 +162,10 @@ APS_HD double aps_obs_logpdf(const aps_model_dev *md, const double *x, const dou
         return aps_fma(-0.5 * t, e, aps_fma(-0.5, x[0], -APS_HALF_LOG_2PI));
     }
     double acc = md->obs_const;
-    const int dy = md->m.dy;
-    for (int m = 0; m < dy; ++m) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int m = 0; m < DY; ++m) {
         double mean = 0.0;
 #if defined(__CUDA_ARCH__)
 #pragma unroll

@@ -452,7 +452,7 @@ struct Sweep {
     int err;
 };
 
-template <int D, int OBS>
+template <int D, int DY, int OBS>
 void advance_all(Sweep &sw, int64_t t) { /* reweight!: src/container.jl:259-302 -> advance!: src/pgas.jl:53-89 */
     const int64_t N = sw.N;
     const bool hasref = sw.ref != nullptr;
@@ -476,18 +476,27 @@ void advance_all(Sweep &sw, int64_t t) { /* reweight!: src/container.jl:259-302 
             }
         }
         for (int k = 0; k < D; ++k) xt[(size_t)i * D + k] = x[k];
-        sw.logw[(size_t)i] += aps_obs_logpdf<D, OBS>(&sw.md, x, y); /* increase_logweight!, container.jl:279 */
+        sw.logw[(size_t)i] += aps_obs_logpdf<D, DY, OBS>(&sw.md, x, y); /* increase_logweight!, container.jl:279 */
     }
 }
 
 typedef void (*advance_fn)(Sweep &, int64_t);
+template <int D, int OBS>
+advance_fn pick_adv_dy(int dy) {
+    switch (dy) {
+        case 1: return advance_all<D, 1, OBS>;
+        case 2: return advance_all<D, 2, OBS>;
+        case 3: return advance_all<D, 3, OBS>;
+        default: return advance_all<D, 4, OBS>;
+    }
+}
 template <int OBS>
-advance_fn pick_adv(int d) {
+advance_fn pick_adv(int d, int dy) {
     switch (d) {
-        case 1: return advance_all<1, OBS>;
-        case 2: return advance_all<2, OBS>;
-        case 3: return advance_all<3, OBS>;
-        default: return advance_all<4, OBS>;
+        case 1: return pick_adv_dy<1, OBS>(dy);
+        case 2: return pick_adv_dy<2, OBS>(dy);
+        case 3: return pick_adv_dy<3, OBS>(dy);
+        default: return pick_adv_dy<4, OBS>(dy);
     }
 }
 
@@ -661,9 +670,9 @@ int orc_sweep(const aps_config *cfg, const double *Y, uint64_t seed, const doubl
 
     advance_fn adv;
     switch (cfg->model.obs_kind) {
-        case APS_OBS_LINEAR_GAUSS: adv = pick_adv<APS_OBS_LINEAR_GAUSS>(sw.d); break;
-        case APS_OBS_STOCH_VOL: adv = pick_adv<APS_OBS_STOCH_VOL>(sw.d); break;
-        default: adv = pick_adv<APS_OBS_CONST>(sw.d); break;
+        case APS_OBS_LINEAR_GAUSS: adv = pick_adv<APS_OBS_LINEAR_GAUSS>(sw.d, sw.dy); break;
+        case APS_OBS_STOCH_VOL: adv = pick_adv<APS_OBS_STOCH_VOL>(sw.d, 1); break;
+        default: adv = pick_adv<APS_OBS_CONST>(sw.d, 1); break;
     }
     const bool bare = cfg->ess_threshold != cfg->ess_threshold; /* NaN: bare resampler function */
     double logev = 0.0;

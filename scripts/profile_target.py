@@ -16,5 +16,7 @@ if mode in ("both", "sweep"):
     h.sweep_profiled(1)   # plain launches (no graph) so ncu sees every kernel
     le, ms, n = h.sweep_profiled(2)
     print("sweep", le, ms, n)
+if mode == "resample_small":
+    print("isolated-small", _lib.bench_resample(_abi.RESAMPLE_SYSTEMATIC, 1 << 20, iters=2, flush_l2=False))
 if mode in ("both", "resample"):
     print("isolated", _lib.bench_resample(_abi.RESAMPLE_SYSTEMATIC, 1 << 25, iters=2, flush_l2=True))
