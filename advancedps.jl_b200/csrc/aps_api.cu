@@ -157,6 +157,11 @@ struct aps_handle {
     cudaEvent_t ev0, ev1;
     SweepParams *d_sp;
     double *d_ref, *d_traj, *d_Y, *d_scratch;  // d_scratch: N x d doubles for accessors
+    // multinomial / residual resampling scratch
+    u64 *d_cum, *d_rq;
+    int *d_counts, *d_tile_count, *d_tile_cprefix;
+    ResidualState *d_rs;   // one per decision point
+    unsigned *d_done2;     // one per decision point
     SweepParams *h_sp;                          // pinned
     SweepState *h_st;                           // pinned
     cudaGraphExec_t graph;
@@ -189,6 +194,13 @@ static void free_handle(aps_handle *h) {
     cudaFree(h->d_traj);
     cudaFree(h->d_Y);
     cudaFree(h->d_scratch);
+    cudaFree(h->d_cum);
+    cudaFree(h->d_rq);
+    cudaFree(h->d_counts);
+    cudaFree(h->d_tile_count);
+    cudaFree(h->d_tile_cprefix);
+    cudaFree(h->d_rs);
+    cudaFree(h->d_done2);
     if (h->h_sp) cudaFreeHost(h->h_sp);
     if (h->h_st) cudaFreeHost(h->h_st);
     if (h->ev0) cudaEventDestroy(h->ev0);
@@ -206,8 +218,6 @@ extern "C" int aps_create(const aps_config *cfg, aps_handle **out) {
     if (cfg->sampler < APS_SMC || cfg->sampler > APS_PGAS) return fail(APS_ERR_INVALID, "aps_create: unknown sampler");
     if (cfg->resampler < APS_RESAMPLE_MULTINOMIAL || cfg->resampler > APS_RESAMPLE_SYSTEMATIC)
         return fail(APS_ERR_INVALID, "aps_create: unknown resampler");
-    if (cfg->resampler == APS_RESAMPLE_MULTINOMIAL || cfg->resampler == APS_RESAMPLE_RESIDUAL)
-        return fail(APS_ERR_INVALID, "aps_create: multinomial / residual resampling inside the sweep is not built yet");
     if (cfg->sampler != APS_SMC && !cfg->keep_history)
         return fail(APS_ERR_INVALID, "aps_create: PG / PGAS need keep_history = 1 (trajectory extraction)");
     if (cfg->world_size != 1 || cfg->rank != 0)
@@ -266,6 +276,15 @@ extern "C" int aps_create(const aps_config *cfg, aps_handle **out) {
     CUH(cudaMalloc(&h->d_traj, sizeof(double) * (size_t)T * d));
     CUH(cudaMalloc(&h->d_Y, sizeof(double) * (size_t)T * c.dy));
     CUH(cudaMalloc(&h->d_scratch, sizeof(double) * (size_t)N * d));
+    if (cfg->resampler == APS_RESAMPLE_MULTINOMIAL || cfg->resampler == APS_RESAMPLE_RESIDUAL) {
+        CUH(cudaMalloc(&h->d_cum, sizeof(u64) * (size_t)c.NS));
+        CUH(cudaMalloc(&h->d_counts, sizeof(int) * (size_t)c.NS));
+        CUH(cudaMalloc(&h->d_tile_count, sizeof(int) * (size_t)c.num_tiles));
+        CUH(cudaMalloc(&h->d_tile_cprefix, sizeof(int) * (size_t)c.num_tiles));
+        CUH(cudaMalloc(&h->d_rs, sizeof(ResidualState) * (size_t)(T + 2)));
+        CUH(cudaMalloc(&h->d_done2, sizeof(unsigned) * (size_t)(T + 2)));
+        if (cfg->resampler == APS_RESAMPLE_RESIDUAL) CUH(cudaMalloc(&h->d_rq, sizeof(u64) * (size_t)c.NS));
+    }
     CUH(cudaMallocHost(&h->h_sp, sizeof(SweepParams)));
     CUH(cudaMallocHost(&h->h_st, sizeof(SweepState)));
     CUH(cudaMemset(c.plan, 0, sizeof(StepPlan) * (size_t)(T + 2)));
@@ -338,6 +357,10 @@ static long long enqueue_sweep(aps_handle *h, LaunchProf *prof = nullptr) {
         ++n;                             \
     } while (0)
     cudaMemsetAsync(c.acc, 0, sizeof(StepAcc) * (size_t)(c.T + 2), st);
+    if (h->d_rs) {
+        cudaMemsetAsync(h->d_rs, 0, sizeof(ResidualState) * (size_t)(c.T + 2), st);
+        cudaMemsetAsync(h->d_done2, 0, sizeof(unsigned) * (size_t)(c.T + 2), st);
+    }
     k_init_sweep<<<1, 32, 0, st>>>(c);
     ++n;
     const int gp = stride_grid(c.N);
@@ -352,7 +375,39 @@ static long long enqueue_sweep(aps_handle *h, LaunchProf *prof = nullptr) {
     for (long long t = 1; t <= c.T; ++t) {
         APS_LAUNCH(0, h->f_prop<<<gk1, APS_K1_THREADS, 0, st>>>(c, t, x_slab(t), x_slab(t - 1), anc_slab(t - 1)));
         APS_LAUNCH(1, k_normalise<IN_LOGW><<<gt, APS_THREADS, 0, st>>>(c, c.logw, t));
-        APS_LAUNCH(2, h->f_res<<<gt, APS_THREADS, APS_K3_DYN_SMEM, st>>>(c, t, anc_slab(t), h->tmap_q));
+        if (c.resampler == APS_RESAMPLE_SYSTEMATIC || c.resampler == APS_RESAMPLE_STRATIFIED) {
+            APS_LAUNCH(2, h->f_res<<<gt, APS_THREADS, APS_K3_DYN_SMEM, st>>>(c, t, anc_slab(t), h->tmap_q));
+        } else {
+            MultiArgs a;
+            memset(&a, 0, sizeof(a));
+            a.cum = h->d_cum;
+            a.counts = h->d_counts;
+            a.tile_count = h->d_tile_count;
+            a.tile_cprefix = h->d_tile_cprefix;
+            a.tile_prefix = c.tile_prefix;
+            a.plan = c.plan + t;
+            a.N = c.N;
+            a.num_tiles = c.num_tiles;
+            a.step = t;
+            if (c.resampler == APS_RESAMPLE_MULTINOMIAL) {
+                a.qsrc = c.q;
+                a.wplan = c.plan + t;
+                a.n_draws = &c.plan[t].n;
+                cudaMemsetAsync(h->d_counts, 0, sizeof(int) * (size_t)c.N, st);
+                cudaMemsetAsync(h->d_tile_count, 0, sizeof(int) * (size_t)c.num_tiles, st);
+            } else {
+                a.qsrc = h->d_rq;
+                a.wplan = c.plan + c.T + 1;
+                a.n_draws = &h->d_rs[t].n_rest;
+                APS_LAUNCH(2, k_residual_split<<<gt, APS_THREADS, 0, st>>>(a, c.q, h->d_rq, h->d_rs + t));
+                APS_LAUNCH(2, k_residual_weights<<<gt, APS_THREADS, 0, st>>>(a, h->d_rq, h->d_rs + t, c.tile_sum, c.tile_prefix,
+                                                                           c.plan + c.T + 1, h->d_done2 + t, &c.st->err));
+            }
+            APS_LAUNCH(2, k_cumsum<<<gt, APS_THREADS, 0, st>>>(a));
+            APS_LAUNCH(2, k_multi_search<1><<<gp, APS_K1_THREADS, 0, st>>>(a, &h->d_sp->key));
+            APS_LAUNCH(2, k_scan_tile_counts<<<1, APS_THREADS, 0, st>>>(a, nullptr));
+            APS_LAUNCH(2, k_expand_counts<<<gt, APS_THREADS, 0, st>>>(a, anc_slab(t), 1));
+        }
         if (c.sampler == APS_PGAS && t >= 2 && t <= c.T - 1) {
             APS_LAUNCH(3, h->f_pmax<<<gp, APS_K1_THREADS, 0, st>>>(c, t, x_slab(t - 1), anc_slab(t - 1), anc_slab(t)));
             APS_LAUNCH(3, h->f_psel<<<gt, APS_THREADS, 0, st>>>(c, t, x_slab(t - 1), anc_slab(t - 1), anc_slab(t)));
@@ -580,8 +635,13 @@ struct OpWorkspace {
     u64 *d_q = nullptr, *tile_sum = nullptr, *tile_s1 = nullptr, *tile_s2 = nullptr, *tile_prefix = nullptr;
     int32_t *d_idx32 = nullptr;
     long long *d_idx64 = nullptr;
+    u64 *d_cum = nullptr, *d_rq = nullptr;
+    int *d_counts = nullptr, *d_tile_count = nullptr, *d_tile_cprefix = nullptr;
+    ResidualState *d_rs = nullptr;
+    unsigned *d_done2 = nullptr;
     StepAcc *acc = nullptr;
-    StepPlan *plan = nullptr;
+    StepPlan *plan = nullptr, *plan2 = nullptr;
+    int *d_err = nullptr;
     SweepState *st = nullptr;
     SweepParams *sp = nullptr;
 };
@@ -592,12 +652,17 @@ static int ws_reserve(OpWorkspace &w, long long m, long long n) {
         CU(cudaStreamCreateWithFlags(&w.stream, cudaStreamNonBlocking));
         CU(cudaMalloc(&w.acc, sizeof(StepAcc)));
         CU(cudaMalloc(&w.plan, sizeof(StepPlan)));
+        CU(cudaMalloc(&w.plan2, sizeof(StepPlan)));
+        CU(cudaMalloc(&w.d_err, sizeof(int)));
         CU(cudaMalloc(&w.st, sizeof(SweepState)));
         CU(cudaMalloc(&w.sp, sizeof(SweepParams)));
+        CU(cudaMalloc(&w.d_rs, sizeof(ResidualState)));
+        CU(cudaMalloc(&w.d_done2, sizeof(unsigned)));
     }
     if (m > w.cap_m) {
         cudaFree(w.d_in); cudaFree(w.d_wout); cudaFree(w.d_q);
         cudaFree(w.tile_sum); cudaFree(w.tile_s1); cudaFree(w.tile_s2); cudaFree(w.tile_prefix);
+        cudaFree(w.d_cum); cudaFree(w.d_rq); cudaFree(w.d_counts); cudaFree(w.d_tile_count); cudaFree(w.d_tile_cprefix);
         w.cap_m = 0;
         const long long nt = (m + APS_TILE - 1) / APS_TILE;
         CU(cudaMalloc(&w.d_in, sizeof(double) * (size_t)m));
@@ -607,6 +672,11 @@ static int ws_reserve(OpWorkspace &w, long long m, long long n) {
         CU(cudaMalloc(&w.tile_s1, sizeof(u64) * (size_t)nt));
         CU(cudaMalloc(&w.tile_s2, sizeof(u64) * (size_t)nt));
         CU(cudaMalloc(&w.tile_prefix, sizeof(u64) * (size_t)nt));
+        CU(cudaMalloc(&w.d_cum, sizeof(u64) * (size_t)(m + 32)));
+        CU(cudaMalloc(&w.d_rq, sizeof(u64) * (size_t)(m + 32)));
+        CU(cudaMalloc(&w.d_counts, sizeof(int) * (size_t)(m + 32)));
+        CU(cudaMalloc(&w.d_tile_count, sizeof(int) * (size_t)nt));
+        CU(cudaMalloc(&w.d_tile_cprefix, sizeof(int) * (size_t)nt));
         w.cap_m = m;
     }
     if (n > w.cap_n) {
@@ -686,8 +756,8 @@ extern "C" int aps_resample(int kind, const double *wts, int64_t m, int64_t n, u
     if (!wts || !idx_out) return fail(APS_ERR_INVALID, "aps_resample: null argument");
     if (m <= 0) return fail(APS_ERR_INVALID, "weight vector is empty");  // src/resampling.jl:103,154
     if (m > 2147483647LL || n < 0 || n > 2147483647LL) return fail(APS_ERR_INVALID, "aps_resample: size out of range");
-    if (kind != APS_RESAMPLE_SYSTEMATIC && kind != APS_RESAMPLE_STRATIFIED)
-        return fail(APS_ERR_INVALID, "aps_resample: multinomial / residual are not built yet");
+    if (kind < APS_RESAMPLE_MULTINOMIAL || kind > APS_RESAMPLE_SYSTEMATIC)
+        return fail(APS_ERR_INVALID, "aps_resample: unknown resampler kind");
     if (ctr >= (1ull << 40)) return fail(APS_ERR_INVALID, "aps_resample: ctr must be < 2^40");
     if (n == 0) return APS_OK;
     OpWorkspace &w = g_ws;
@@ -700,11 +770,54 @@ extern "C" int aps_resample(int kind, const double *wts, int64_t m, int64_t n, u
     rc = op_normalise<IN_W>(w, c, wts, m, key, ctr, &p);
     if (rc) return rc;
     if (p.err) return fail(APS_ERR_WEIGHTS, "sample could not be selected (are the weights normalized?)");
-    rc = make_q_tensormap(&w.tmap_q, w.d_q, c.NS);
-    if (rc) return rc;
-    rc = enable_k3_smem();
-    if (rc) return rc;
-    pick_resample(kind)<<<(int)c.num_tiles, APS_THREADS, APS_K3_DYN_SMEM, w.stream>>>(c, 0, w.d_idx32, w.tmap_q);
+    if (kind == APS_RESAMPLE_SYSTEMATIC || kind == APS_RESAMPLE_STRATIFIED) {
+        rc = make_q_tensormap(&w.tmap_q, w.d_q, c.NS);
+        if (rc) return rc;
+        rc = enable_k3_smem();
+        if (rc) return rc;
+        pick_resample(kind)<<<(int)c.num_tiles, APS_THREADS, APS_K3_DYN_SMEM, w.stream>>>(c, 0, w.d_idx32, w.tmap_q);
+    } else {
+        const int gt = (int)c.num_tiles;
+        MultiArgs a;
+        memset(&a, 0, sizeof(a));
+        a.cum = w.d_cum;
+        a.counts = w.d_counts;
+        a.tile_count = w.d_tile_count;
+        a.tile_cprefix = w.d_tile_cprefix;
+        a.tile_prefix = w.tile_prefix;
+        a.plan = w.plan;
+        a.N = m;
+        a.num_tiles = c.num_tiles;
+        a.step = (long long)ctr;
+        a.out32 = w.d_idx32;
+        if (kind == APS_RESAMPLE_MULTINOMIAL) {
+            a.qsrc = w.d_q;
+            a.wplan = w.plan;
+            a.n_draws = &w.plan->n;
+        } else {
+            // deterministic copies first (sorted), then the residual draws in draw order (src/resampling.jl:62-78)
+            CU(cudaMemsetAsync(w.d_err, 0, sizeof(int), w.stream));
+            CU(cudaMemsetAsync(w.d_rs, 0, sizeof(ResidualState), w.stream));
+            CU(cudaMemsetAsync(w.d_done2, 0, sizeof(unsigned), w.stream));
+            a.qsrc = w.d_rq;
+            a.n_draws = &w.d_rs->n_rest;
+            a.out_offset = &w.d_rs->n_det;
+            k_residual_split<<<gt, APS_THREADS, 0, w.stream>>>(a, w.d_q, w.d_rq, w.d_rs);
+            k_scan_tile_counts<<<1, APS_THREADS, 0, w.stream>>>(a, nullptr);
+            k_expand_counts<<<gt, APS_THREADS, 0, w.stream>>>(a, w.d_idx32, 0);
+            a.wplan = w.plan2;
+            k_residual_weights<<<gt, APS_THREADS, 0, w.stream>>>(a, w.d_rq, w.d_rs, w.tile_sum, w.tile_prefix, w.plan2,
+                                                                w.d_done2, w.d_err);
+        }
+        k_cumsum<<<gt, APS_THREADS, 0, w.stream>>>(a);
+        k_multi_search<0><<<stride_grid(n), APS_K1_THREADS, 0, w.stream>>>(a, &w.sp->key);
+    }
+    if (kind == APS_RESAMPLE_RESIDUAL) {
+        int herr = 0;
+        CU(cudaMemcpyAsync(&herr, w.d_err, sizeof(int), cudaMemcpyDeviceToHost, w.stream));
+        CU(cudaStreamSynchronize(w.stream));
+        if (herr) return fail(APS_ERR_WEIGHTS, "sample could not be selected (residual weights vanish)");
+    }
     const bool dev_out = is_device_ptr(idx_out);
     long long *d_out = dev_out ? (long long *)idx_out : w.d_idx64;
     k_to_one_based<<<stride_grid(n), APS_THREADS, 0, w.stream>>>(w.d_idx32, n, d_out);

@@ -568,6 +568,245 @@ __global__ void __launch_bounds__(APS_THREADS, 8) k_resample(const __grid_consta
     if (blockIdx.x == gridDim.x - 1 && tid == 0 && n < N) anc_out[N - 1] = (int32_t)(N - 1);
 }
 
+// ---------------------------------------------------------------- multinomial / residual resampling
+// resample_multinomial (src/resampling.jl:31-35): child i draws U_i and takes the first parent j
+// with C_j > floor(U_i Q / 2^53) -- i.i.d. categorical draws by inverse CDF on the integer
+// weights (upstream uses Distributions' alias table; same law). resample_residual (:53-81):
+// floor(n q_j / Q) copies of j, the rest i.i.d. on the residuals n q_j - floor(.) Q (shifted so
+// their sum fits 62 bits). Inside the sweep only the offspring counts matter (children are laid
+// out grouped by parent, src/container.jl:185-217), so draws are histogrammed with
+// warp-aggregated integer atomics and expanded like the systematic case.
+struct MultiArgs {
+    const u64 *qsrc;        // integer weights the draws are made on (q, or shifted residuals)
+    u64 *cum;               // inclusive cumulative sums of qsrc (global)
+    const u64 *tile_prefix; // exclusive tile prefix of qsrc
+    int *counts;            // offspring count per parent
+    int *tile_count;        // offspring count per tile (becomes its exclusive scan)
+    int *tile_cprefix;
+    const StepPlan *plan;   // decision point plan (resampled / err / n)
+    const StepPlan *wplan;  // plan carrying Q of qsrc (plan itself, or the residual stage plan)
+    const long long *n_draws; // device: number of i.i.d. draws (n, or the residual count Rc)
+    int32_t *out32;         // operator level: 0-based parent of draw r goes to out32[out_offset + r]
+    const long long *out_offset;
+    long long N;
+    long long num_tiles;
+    long long step;         // Philox step counter of the draws
+};
+
+// inclusive cumulative sums of one tile of qsrc (thread-blocked, 16 per thread)
+__global__ void __launch_bounds__(APS_THREADS) k_cumsum(const __grid_constant__ MultiArgs a) {
+    __shared__ u64 red[APS_WARPS];
+    if (!a.plan->resampled || a.plan->err) return;
+    const long long base = (long long)blockIdx.x * APS_TILE + (long long)threadIdx.x * APS_IPT;
+    u64 cum[APS_IPT];
+#pragma unroll
+    for (int r = 0; r < APS_IPT; ++r) cum[r] = (base + r < a.N) ? a.qsrc[base + r] : 0ull;
+#pragma unroll
+    for (int r = 1; r < APS_IPT; ++r) cum[r] += cum[r - 1];
+    u64 tot;
+    const u64 excl = block_excl_scan_u64<APS_WARPS>(cum[APS_IPT - 1], red, &tot) + a.tile_prefix[blockIdx.x];
+#pragma unroll
+    for (int r = 0; r < APS_IPT; ++r)
+        if (base + r < a.N) a.cum[base + r] = excl + cum[r];
+}
+
+// one i.i.d. draw per thread: two-level binary search (tile prefix, then the tile's cumulative sums)
+template <int TO_COUNTS>
+__global__ void __launch_bounds__(APS_K1_THREADS) k_multi_search(const __grid_constant__ MultiArgs a, const u64 *keyp) {
+    if (!a.plan->resampled || a.plan->err) return;
+    const long long nd = *a.n_draws;
+    const u64 Q = a.wplan->Q;
+    const u64 key = *keyp;
+    const long long off = a.out_offset ? *a.out_offset : 0;
+    for (long long i = (long long)blockIdx.x * APS_K1_THREADS + threadIdx.x; i < nd;
+         i += (long long)gridDim.x * APS_K1_THREADS) {
+        uint64_t w0, w1;
+        aps_philox2x64((u64)i, aps_ctr1((u64)a.step, APS_DOM_RESAMPLE, 0), key, &w0, &w1);
+        const u64 tau = floor_uq53(aps_u53(w0), Q);
+        // last tile whose exclusive prefix is <= tau
+        long long lo = 0, hi = a.num_tiles - 1;
+        while (lo < hi) {
+            const long long mid = (lo + hi + 1) >> 1;
+            if (a.tile_prefix[mid] <= tau) lo = mid;
+            else hi = mid - 1;
+        }
+        const long long tile = lo;
+        long long jl = tile * APS_TILE, jh = jl + APS_TILE < a.N ? jl + APS_TILE : a.N;
+        --jh;  // first j in [jl, jh] with cum[j] > tau (exists unless trailing zero weights)
+        while (jl < jh) {
+            const long long mid = (jl + jh) >> 1;
+            if (a.cum[mid] > tau) jh = mid;
+            else jl = mid + 1;
+        }
+        if (TO_COUNTS) {
+            // warp-aggregated histogram: lanes that drew the same parent issue one atomic
+            const unsigned act = __activemask();
+            const unsigned same = __match_any_sync(act, (int)jl);
+            if ((int)(__ffs(same) - 1) == (int)(threadIdx.x & 31)) {
+                atomicAdd(&a.counts[jl], __popc(same));
+            }
+            const unsigned samet = __match_any_sync(act, (int)tile);
+            if ((int)(__ffs(samet) - 1) == (int)(threadIdx.x & 31)) atomicAdd(&a.tile_count[tile], __popc(samet));
+        } else {
+            a.out32[off + i] = (int32_t)jl;
+        }
+    }
+}
+
+// exclusive scan of the per-tile offspring counts (one block)
+__global__ void __launch_bounds__(APS_THREADS) k_scan_tile_counts(const __grid_constant__ MultiArgs a, long long *total_out) {
+    __shared__ u64 red[APS_WARPS];
+    if (!a.plan->resampled || a.plan->err) return;
+    const long long nt = a.num_tiles;
+    const long long per = (nt + APS_THREADS - 1) / APS_THREADS;
+    const long long lo = (long long)threadIdx.x * per;
+    const long long hi = lo + per < nt ? lo + per : nt;
+    u64 acc = 0;
+    for (long long k = lo; k < hi; ++k) acc += (u64)a.tile_count[k];
+    u64 tot;
+    u64 run = block_excl_scan_u64<APS_WARPS>(acc, red, &tot);
+    for (long long k = lo; k < hi; ++k) {
+        a.tile_cprefix[k] = (int)run;
+        run += (u64)a.tile_count[k];
+    }
+    if (threadIdx.x == 0 && total_out) *total_out = (long long)tot;
+}
+
+// offspring counts -> sorted ancestor indices (same expand machinery as k_resample)
+__global__ void __launch_bounds__(APS_THREADS) k_expand_counts(const __grid_constant__ MultiArgs a, int32_t *__restrict__ anc_out,
+                                                               const int identity_if_not_resampled) {
+    __shared__ u64 red[APS_WARPS];
+    __shared__ __align__(16) int own[APS_CAP];
+    __shared__ int wmax[APS_WARPS];
+    const int tid = threadIdx.x;
+    const long long base = (long long)blockIdx.x * APS_TILE;
+    if (!a.plan->resampled || a.plan->err) {
+        if (identity_if_not_resampled) {
+#pragma unroll
+            for (int r = 0; r < APS_IPT; ++r) {
+                const long long i = base + r * APS_THREADS + tid;
+                if (i < a.N) anc_out[i] = (int32_t)i;
+            }
+        }
+        return;
+    }
+    const long long i0 = base + (long long)tid * APS_IPT;
+    int khi[APS_IPT];
+#pragma unroll
+    for (int r = 0; r < APS_IPT; ++r) khi[r] = (i0 + r < a.N) ? a.counts[i0 + r] : 0;
+#pragma unroll
+    for (int r = 1; r < APS_IPT; ++r) khi[r] += khi[r - 1];
+    u64 tot;
+    const int kA = a.tile_cprefix[blockIdx.x];
+    const int excl = (int)block_excl_scan_u64<APS_WARPS>((u64)khi[APS_IPT - 1], red, &tot) + kA;
+    const int kB = kA + (int)tot;
+#pragma unroll
+    for (int r = 0; r < APS_IPT; ++r) khi[r] += excl;
+    expand_tile_general(khi, excl, kA, kB, (int)base, anc_out, own, wmax);
+    const long long n = a.plan->n;
+    if (blockIdx.x == gridDim.x - 1 && tid == 0 && n < a.N && identity_if_not_resampled) anc_out[a.N - 1] = (int32_t)(a.N - 1);
+}
+
+// residual stage 1: deterministic copies d_j = floor(n q_j / Q) and raw residuals n q_j - d_j Q
+struct ResidualState {
+    u64 sum_d;         // total deterministic copies (atomic)
+    long long n_rest;  // Rc = n - sum_d
+    long long n_det;   // sum_d as a signed count (output offset of the residual draws)
+    int shift;         // ceil_log2(Rc + 1)
+    unsigned done_ctr;
+};
+
+__global__ void __launch_bounds__(APS_THREADS) k_residual_split(const __grid_constant__ MultiArgs a, const u64 *__restrict__ q,
+                                                                u64 *__restrict__ rq, ResidualState *rs) {
+    __shared__ u64 red[APS_WARPS];
+    if (!a.plan->resampled || a.plan->err) return;
+    const u64 Q = a.plan->Q;
+    const int n = (int)a.plan->n;
+    const double ratio = a.plan->ratio;  // 2^24 n / Q
+    const int guard = a.plan->guard;
+    const long long base = (long long)blockIdx.x * APS_TILE;
+    u64 sd = 0;
+#pragma unroll 4
+    for (int r = 0; r < APS_IPT; ++r) {
+        const long long j = base + r * APS_THREADS + threadIdx.x;
+        if (j < a.N) {
+            const u64 qj = q[j];
+            // F = first i in [0,n] with !(i < n && i Q <= qj n); d = F - 1, or n when qj == Q
+            bool u = false;
+            int F = first_above_est((double)qj * ratio, n, guard, &u);
+            if (u) F = first_above_exact(F, qj, Q, 0ull, n);
+            int d = F - 1;
+            if (F == n && le_128(mul_64_64((u64)n, Q), mul_64_64(qj, (u64)n))) d = n;
+            a.counts[j] = d;
+            rq[j] = qj * (u64)n - (u64)d * Q;  // < Q: exact modulo 2^64
+            sd += (u64)d;
+        }
+    }
+    sd = block_sum_u64<APS_WARPS>(sd, red);
+    if (threadIdx.x == 0) {
+        a.tile_count[blockIdx.x] = (int)sd;
+        atomicAdd(&rs->sum_d, sd);
+        __threadfence();
+        const unsigned ticket = atomicAdd(&rs->done_ctr, 1u);
+        if (ticket == gridDim.x - 1) {
+            __threadfence();
+            const u64 tot = atomicAdd(&rs->sum_d, 0ull);
+            const long long rc = (long long)n - (long long)tot;
+            rs->n_rest = rc;
+            rs->n_det = (long long)tot;
+            rs->shift = aps_ceil_log2((uint64_t)rc + 1);
+        }
+    }
+}
+
+// residual stage 2: shifted residual weights, their tile totals and exclusive tile prefix
+__global__ void __launch_bounds__(APS_THREADS) k_residual_weights(const __grid_constant__ MultiArgs a, u64 *__restrict__ rq,
+                                                                  const ResidualState *rs, u64 *tile_sum, u64 *tile_prefix,
+                                                                  StepPlan *wplan, unsigned *done_ctr, int *err_out) {
+    __shared__ u64 red[APS_WARPS];
+    __shared__ unsigned s_last;
+    if (!a.plan->resampled || a.plan->err) return;
+    if (rs->n_rest <= 0) return;
+    const int sh = rs->shift;
+    const long long base = (long long)blockIdx.x * APS_TILE;
+    u64 s0 = 0;
+#pragma unroll
+    for (int r = 0; r < APS_IPT; ++r) {
+        const long long j = base + r * APS_THREADS + threadIdx.x;
+        if (j < a.N) {
+            const u64 v = rq[j] >> sh;
+            rq[j] = v;
+            s0 += v;
+        }
+    }
+    s0 = block_sum_u64<APS_WARPS>(s0, red);
+    if (threadIdx.x == 0) {
+        tile_sum[blockIdx.x] = s0;
+        __threadfence();
+        const unsigned ticket = atomicAdd(done_ctr, 1u);
+        s_last = (ticket == gridDim.x - 1) ? 1u : 0u;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    const long long nt = a.num_tiles;
+    const long long per = (nt + APS_THREADS - 1) / APS_THREADS;
+    const long long lo = (long long)threadIdx.x * per;
+    const long long hi = lo + per < nt ? lo + per : nt;
+    u64 acc = 0;
+    for (long long k = lo; k < hi; ++k) acc += __ldcg(&tile_sum[k]);
+    u64 tot;
+    u64 run = block_excl_scan_u64<APS_WARPS>(acc, red, &tot);
+    for (long long k = lo; k < hi; ++k) {
+        tile_prefix[k] = run;
+        run += __ldcg(&tile_sum[k]);
+    }
+    if (threadIdx.x == 0) {
+        wplan->Q = tot;
+        if (tot == 0 && err_out) *err_out = APS_ERR_WEIGHTS;
+    }
+}
+
 // ---------------------------------------------------------------- categorical draw (PGAS ancestor, final pick)
 // lw_i for the PGAS ancestor weights: log f(X_ref[c-1] | X_i[c-2]) + logW_i   (src/pgas.jl:26-46)
 // xpp: states of time s-1 (= c-2); anc_cur: ancestors of set s (= c-1)

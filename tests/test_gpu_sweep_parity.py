@@ -71,6 +71,28 @@ def test_lg1_stratified():
     assert_sweep_equal(cfg, ro, h, le)
 
 
+@pytest.mark.parametrize("resampler", [_abi.RESAMPLE_MULTINOMIAL, _abi.RESAMPLE_RESIDUAL])
+@pytest.mark.parametrize("thr", [float("nan"), 0.5])
+def test_lg1_multinomial_residual(resampler, thr):
+    cfg, Y, ro, h, le = run_both(models.linear_gaussian(), 6007, 14, 21, 0xDA7A0001, resampler=resampler,
+                                 ess_threshold=thr)
+    assert_sweep_equal(cfg, ro, h, le)
+
+
+@pytest.mark.parametrize("resampler", [_abi.RESAMPLE_MULTINOMIAL, _abi.RESAMPLE_RESIDUAL, _abi.RESAMPLE_STRATIFIED])
+def test_pg_conditional_other_resamplers(resampler):
+    m = models.linear_gaussian()
+    N, T = 3000, 8
+    cfg = _abi.make_config(m, N, T, sampler=_abi.SAMPLER_PG, resampler=resampler, ess_threshold=0.5)
+    _, Y = O.simulate_data(m, T, 3)
+    ref = np.linspace(0.2, 0.6, T).reshape(T, 1)
+    ro = O.sweep(cfg, Y, 5, ref_traj=ref, mode=O.CANON)
+    h = _lib.Handle(cfg)
+    h.set_observations(Y)
+    le = h.sweep(5, ref_traj=ref)
+    assert_sweep_equal(cfg, ro, h, le)
+
+
 def test_lg4_smc():
     cfg, Y, ro, h, le = run_both(models.lg4(), 20000, 15, 7, 0xDA7A0003)
     assert_sweep_equal(cfg, ro, h, le)
