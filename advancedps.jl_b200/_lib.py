@@ -87,7 +87,9 @@ class Handle:
         self.cfg = cfg
         self._h = C.c_void_p()
         check(lib().aps_create(C.byref(cfg), C.byref(self._h)))
-        self.N, self.T, self.d, self.dy = cfg.n_particles, cfg.n_steps, cfg.model.d, cfg.model.dy
+        # N: slots held by this handle (the local shard when world_size > 1); Ng: global particle count
+        self.Ng, self.rank, self.world = cfg.n_particles, cfg.rank, cfg.world_size
+        self.N, self.T, self.d, self.dy = cfg.n_particles // cfg.world_size, cfg.n_steps, cfg.model.d, cfg.model.dy
 
     def close(self):
         if self._h:
@@ -99,6 +101,17 @@ class Handle:
             self.close()
         except Exception:
             pass
+
+    # ---- multi-GPU plumbing: opaque blobs the host exchanges between ranks
+    def ipc_export(self):
+        blob = np.zeros(_abi.IPC_BLOB_BYTES, dtype=np.uint8)
+        check(lib().aps_ipc_export(self._h, ptr(blob)))
+        return blob
+
+    def ipc_import(self, blobs):
+        blobs = np.ascontiguousarray(np.stack(blobs), dtype=np.uint8)
+        assert blobs.shape == (self.world, _abi.IPC_BLOB_BYTES)
+        check(lib().aps_ipc_import(self._h, ptr(blobs)))
 
     def set_observations(self, Y):
         Y = np.ascontiguousarray(Y, dtype=np.float64).reshape(self.T, self.dy)

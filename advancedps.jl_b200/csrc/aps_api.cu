@@ -3,6 +3,7 @@
 // points and the resample-kernel micro-benchmark. No torch types; plain pointers and sizes.
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <unistd.h>
 #include <string.h>
 #include <math.h>
 #include <mutex>
@@ -166,6 +167,13 @@ struct aps_handle {
     SweepState *h_st;                           // pinned
     cudaGraphExec_t graph;
     bool graph_ready, has_obs, swept, ref_valid;
+    // multi-GPU
+    MailSlot *d_mail;
+    PeerTable *d_peers;
+    void *ipc_opened[3 * APS_MAX_RANKS];
+    int n_ipc_opened;
+    bool comm_ready;
+    unsigned long long epoch;
     float last_ms;
     long long last_launches, graph_nodes;
     CUtensorMap tmap_q;
@@ -201,6 +209,9 @@ static void free_handle(aps_handle *h) {
     cudaFree(h->d_tile_cprefix);
     cudaFree(h->d_rs);
     cudaFree(h->d_done2);
+    for (int i = 0; i < h->n_ipc_opened; ++i) cudaIpcCloseMemHandle(h->ipc_opened[i]);
+    cudaFree(h->d_mail);
+    cudaFree(h->d_peers);
     if (h->h_sp) cudaFreeHost(h->h_sp);
     if (h->h_st) cudaFreeHost(h->h_st);
     if (h->ev0) cudaEventDestroy(h->ev0);
@@ -220,8 +231,17 @@ extern "C" int aps_create(const aps_config *cfg, aps_handle **out) {
         return fail(APS_ERR_INVALID, "aps_create: unknown resampler");
     if (cfg->sampler != APS_SMC && !cfg->keep_history)
         return fail(APS_ERR_INVALID, "aps_create: PG / PGAS need keep_history = 1 (trajectory extraction)");
-    if (cfg->world_size != 1 || cfg->rank != 0)
-        return fail(APS_ERR_INVALID, "aps_create: multi-GPU sharding is not built yet (world_size must be 1)");
+    const int world = cfg->world_size;
+    if (world < 1 || world > APS_MAX_RANKS || cfg->rank < 0 || cfg->rank >= world)
+        return fail(APS_ERR_INVALID, "aps_create: rank / world_size out of range (1..8 ranks)");
+    if (world > 1) {
+        if (cfg->sampler != APS_SMC)
+            return fail(APS_ERR_INVALID, "aps_create: the sharded sweep supports SMC only (PG / PGAS: single GPU)");
+        if (cfg->resampler != APS_RESAMPLE_SYSTEMATIC && cfg->resampler != APS_RESAMPLE_STRATIFIED)
+            return fail(APS_ERR_INVALID, "aps_create: the sharded sweep supports systematic / stratified resampling only");
+        if (N % ((long long)world * 32) != 0)
+            return fail(APS_ERR_INVALID, "aps_create: n_particles must be a multiple of 32 * world_size");
+    }
     aps_handle *h = new aps_handle();
     memset(h, 0, sizeof(*h));
     h->cfg = *cfg;
@@ -244,8 +264,14 @@ extern "C" int aps_create(const aps_config *cfg, aps_handle **out) {
     CUH(cudaEventCreate(&h->ev1));
     DevCtx &c = h->ctx;
     const int d = cfg->model.d;
-    c.N = N;
-    c.NS = (N + 31) & ~31LL;
+    const long long Nl = N / world;  // this rank's shard of the N global particles
+    c.N = Nl;
+    c.Ng = N;
+    c.slot0 = (long long)cfg->rank * Nl;
+    c.rank = cfg->rank;
+    c.world = world;
+    c.peers = nullptr;
+    c.NS = (Nl + 31) & ~31LL;
     c.T = T;
     c.d = d;
     c.dy = cfg->model.dy;
@@ -259,7 +285,7 @@ extern "C" int aps_create(const aps_config *cfg, aps_handle **out) {
     c.n_override = 0;
     c.x_slabs = cfg->keep_history ? T : 2;
     c.anc_slabs = cfg->keep_history ? T + 1 : 2;
-    c.num_tiles = (N + APS_TILE - 1) / APS_TILE;
+    c.num_tiles = (Nl + APS_TILE - 1) / APS_TILE;
     CUH(cudaMalloc(&c.x, sizeof(double) * (size_t)c.x_slabs * d * c.NS));
     CUH(cudaMalloc(&c.anc, sizeof(int32_t) * (size_t)c.anc_slabs * c.NS));
     CUH(cudaMalloc(&c.logw, sizeof(double) * (size_t)c.NS));
@@ -275,7 +301,12 @@ extern "C" int aps_create(const aps_config *cfg, aps_handle **out) {
     CUH(cudaMalloc(&h->d_ref, sizeof(double) * (size_t)T * d));
     CUH(cudaMalloc(&h->d_traj, sizeof(double) * (size_t)T * d));
     CUH(cudaMalloc(&h->d_Y, sizeof(double) * (size_t)T * c.dy));
-    CUH(cudaMalloc(&h->d_scratch, sizeof(double) * (size_t)N * d));
+    CUH(cudaMalloc(&h->d_scratch, sizeof(double) * (size_t)Nl * d));
+    if (world > 1) {
+        CUH(cudaMalloc(&h->d_mail, sizeof(MailSlot) * 3 * APS_MAX_RANKS));
+        CUH(cudaMemset(h->d_mail, 0, sizeof(MailSlot) * 3 * APS_MAX_RANKS));
+        CUH(cudaMalloc(&h->d_peers, sizeof(PeerTable)));
+    }
     if (cfg->resampler == APS_RESAMPLE_MULTINOMIAL || cfg->resampler == APS_RESAMPLE_RESIDUAL) {
         CUH(cudaMalloc(&h->d_cum, sizeof(u64) * (size_t)c.NS));
         CUH(cudaMalloc(&h->d_counts, sizeof(int) * (size_t)c.NS));
@@ -374,7 +405,7 @@ static long long enqueue_sweep(aps_handle *h, LaunchProf *prof = nullptr) {
     auto anc_slab = [&](long long sidx) { return c.anc + ((sidx + c.anc_slabs) % c.anc_slabs) * c.NS; };
     for (long long t = 1; t <= c.T; ++t) {
         APS_LAUNCH(0, h->f_prop<<<gk1, APS_K1_THREADS, 0, st>>>(c, t, x_slab(t), x_slab(t - 1), anc_slab(t - 1)));
-        APS_LAUNCH(1, k_normalise<IN_LOGW><<<gt, APS_THREADS, 0, st>>>(c, c.logw, t));
+        APS_LAUNCH(1, k_normalise<IN_LOGW><<<gt, APS_K2_THREADS, 0, st>>>(c, c.logw, t));
         if (c.resampler == APS_RESAMPLE_SYSTEMATIC || c.resampler == APS_RESAMPLE_STRATIFIED) {
             APS_LAUNCH(2, h->f_res<<<gt, APS_THREADS, APS_K3_DYN_SMEM, st>>>(c, t, anc_slab(t), h->tmap_q));
         } else {
@@ -435,9 +466,11 @@ static int sweep_impl(aps_handle *h, uint64_t master_seed, const double *ref_tra
         }
         has_ref = 1;
     }
+    if (c.world > 1 && !h->comm_ready) return fail(APS_ERR_COMM, "aps_sweep: peers not attached (aps_ipc_export / aps_ipc_import)");
     h->h_sp->key = master_seed;
     h->h_sp->has_ref = has_ref;
     h->h_sp->pad = 0;
+    h->h_sp->epoch = h->epoch++;
     CU(cudaMemcpyAsync(h->d_sp, h->h_sp, sizeof(SweepParams), cudaMemcpyHostToDevice, h->stream));
     LaunchProf prof;
     prof.st = h->stream;
@@ -477,7 +510,9 @@ static int sweep_impl(aps_handle *h, uint64_t master_seed, const double *ref_tra
     }
     h->swept = true;
     if (h->h_st->err)
-        return fail(h->h_st->err, "aps_sweep: particle weights could not be normalised (all -Inf or NaN log-weights)");
+        return fail(h->h_st->err, h->h_st->err == APS_ERR_COMM
+                                      ? "aps_sweep: a peer rank did not answer within the exchange timeout"
+                                      : "aps_sweep: particle weights could not be normalised (all -Inf or NaN log-weights)");
     *logevidence = h->h_st->logev;
     return APS_OK;
 }
@@ -500,6 +535,7 @@ extern "C" int aps_sweep_profiled(aps_handle *h, uint64_t master_seed, const dou
 extern "C" int aps_pick_trajectory(aps_handle *h, double *traj_out, int64_t *index_out) {
     NEED_SWEEP("aps_pick_trajectory");
     if (!h->cfg.keep_history) return fail(APS_ERR_INVALID, "aps_pick_trajectory: handle was created with keep_history = 0");
+    if (h->ctx.world > 1) return fail(APS_ERR_INVALID, "aps_pick_trajectory: not available on a sharded handle yet");
     const DevCtx &c = h->ctx;
     k_pick<<<1, APS_THREADS, 0, h->stream>>>(c, c.T, c.T + 1, APS_DOM_PICK);
     k_backtrace<<<1, 32, 0, h->stream>>>(c, -1, h->d_traj);
@@ -527,7 +563,7 @@ extern "C" int aps_get_weights(aps_handle *h, double *w_out) {
     NEED_SWEEP("aps_get_weights");
     if (!w_out) return fail(APS_ERR_INVALID, "aps_get_weights: null output");
     const DevCtx &c = h->ctx;
-    k_weights_out<<<stride_grid(c.N), APS_THREADS, 0, h->stream>>>(c.q, c.plan + c.T, c.N, c.S, 1, h->d_scratch);
+    k_weights_out<<<stride_grid(c.N), APS_THREADS, 0, h->stream>>>(c.q, c.plan + c.T, c.N, c.Ng, c.S, 1, h->d_scratch);
     CU(cudaMemcpyAsync(w_out, h->d_scratch, sizeof(double) * (size_t)c.N, cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     CU(cudaGetLastError());
@@ -553,6 +589,7 @@ extern "C" int aps_get_final_states(aps_handle *h, double *x_out) {
     NEED_SWEEP("aps_get_final_states");
     if (!x_out) return fail(APS_ERR_INVALID, "aps_get_final_states: null output");
     const DevCtx &c = h->ctx;
+    if (c.world > 1) return fail(APS_ERR_INVALID, "aps_get_final_states: not available on a sharded handle yet");
     k_gather_final<<<stride_grid(c.N), APS_THREADS, 0, h->stream>>>(c, h->d_scratch);
     CU(cudaMemcpyAsync(x_out, h->d_scratch, sizeof(double) * (size_t)c.N * c.d, cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
@@ -566,6 +603,7 @@ extern "C" int aps_get_trajectory(aps_handle *h, int64_t slot, double *traj_out)
     if (!h->cfg.keep_history) return fail(APS_ERR_INVALID, "aps_get_trajectory: handle was created with keep_history = 0");
     const DevCtx &c = h->ctx;
     if (slot < 0 || slot >= c.N) return fail(APS_ERR_INVALID, "aps_get_trajectory: slot out of range");
+    if (c.world > 1) return fail(APS_ERR_INVALID, "aps_get_trajectory: not available on a sharded handle yet");
     k_backtrace<<<1, 32, 0, h->stream>>>(c, slot, h->d_traj);
     CU(cudaMemcpyAsync(traj_out, h->d_traj, sizeof(double) * (size_t)c.T * c.d, cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
@@ -711,6 +749,8 @@ static void op_ctx(OpWorkspace &w, DevCtx &c, long long m, long long n_draw) {
     c.sp = w.sp;
     c.anc = w.d_idx32;
     c.N = m;
+    c.Ng = m;
+    c.world = 1;
     c.NS = (m + 31) & ~31LL;
     c.T = 0;
     c.x_slabs = 1;
@@ -744,7 +784,7 @@ static int op_normalise(OpWorkspace &w, DevCtx &c, const double *in, long long m
     if (c.NS > m) CU(cudaMemsetAsync(w.d_q + m, 0, sizeof(u64) * (size_t)(c.NS - m), w.stream));  // zero-weight padding
     k_vector_max<INPUT><<<stride_grid(m), APS_K1_THREADS, 0, w.stream>>>(d_in, m, w.acc);
     c.ctr_offset = (long long)ctr;
-    k_normalise<INPUT><<<(int)c.num_tiles, APS_THREADS, 0, w.stream>>>(c, d_in, 0);
+    k_normalise<INPUT><<<(int)c.num_tiles, APS_K2_THREADS, 0, w.stream>>>(c, d_in, 0);
     CU(cudaMemcpyAsync(plan_host, w.plan, sizeof(StepPlan), cudaMemcpyDeviceToHost, w.stream));
     CU(cudaStreamSynchronize(w.stream));
     CU(cudaGetLastError());
@@ -877,7 +917,7 @@ extern "C" int aps_softmax(const double *logw, int64_t n, double *w_out) {
     if (p.err) return fail(APS_ERR_WEIGHTS, "aps_softmax: weights not normalisable");
     const bool dev_out = is_device_ptr(w_out);
     double *d_out = dev_out ? w_out : w.d_wout;
-    k_weights_out<<<stride_grid(n), APS_THREADS, 0, w.stream>>>(w.d_q, w.plan, n, c.S, 0, d_out);
+    k_weights_out<<<stride_grid(n), APS_THREADS, 0, w.stream>>>(w.d_q, w.plan, n, n, c.S, 0, d_out);
     if (!dev_out) CU(cudaMemcpyAsync(w_out, w.d_wout, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, w.stream));
     CU(cudaStreamSynchronize(w.stream));
     CU(cudaGetLastError());
@@ -937,7 +977,7 @@ extern "C" int aps_bench_resample(int kind, int64_t n, int iters, int flush_l2, 
     CU(cudaMemsetAsync(w.acc, 0, sizeof(StepAcc), w.stream));
     if (c.NS > n) CU(cudaMemsetAsync(w.d_q + n, 0, sizeof(u64) * (size_t)(c.NS - n), w.stream));
     k_bench_weights<<<stride_grid(n), APS_THREADS, 0, w.stream>>>(w.d_q, n, c.S, seed);
-    k_normalise<IN_Q><<<(int)c.num_tiles, APS_THREADS, 0, w.stream>>>(c, nullptr, 0);
+    k_normalise<IN_Q><<<(int)c.num_tiles, APS_K2_THREADS, 0, w.stream>>>(c, nullptr, 0);
     StepPlan p;
     CU(cudaMemcpyAsync(&p, w.plan, sizeof(p), cudaMemcpyDeviceToHost, w.stream));
     CU(cudaStreamSynchronize(w.stream));
@@ -977,14 +1017,78 @@ extern "C" int aps_bench_resample(int kind, int64_t n, int iters, int flush_l2, 
     return APS_OK;
 }
 
-// ================================================================== multi-GPU plumbing (not built yet)
+// ================================================================== multi-GPU plumbing
+// Blob exchanged between ranks: CUDA IPC handles of the state store, the ancestor store and the
+// mailbox (plus raw pointers, used when both "ranks" live in one process, e.g. in tests).
+struct IpcBlob {
+    unsigned long long magic;
+    long long pid;
+    int device, rank;
+    void *raw[3];
+    cudaIpcMemHandle_t mem[3];
+};
+static_assert(sizeof(IpcBlob) <= APS_IPC_BLOB_BYTES, "IpcBlob must fit the ABI blob");
+
 extern "C" int aps_ipc_export(aps_handle *h, uint8_t *blob_out) {
-    (void)h;
-    (void)blob_out;
-    return fail(APS_ERR_COMM, "aps_ipc_export: multi-GPU sharding is not built yet");
+    if (!h || !blob_out) return fail(APS_ERR_INVALID, "aps_ipc_export: null argument");
+    if (h->ctx.world < 2) return fail(APS_ERR_INVALID, "aps_ipc_export: handle is not sharded (world_size == 1)");
+    CU(cudaSetDevice(h->cfg.device));
+    IpcBlob b;
+    memset(&b, 0, sizeof(b));
+    b.magic = 0x4150534950433031ULL;
+    b.pid = (long long)getpid();
+    b.device = h->cfg.device;
+    b.rank = h->ctx.rank;
+    b.raw[0] = h->ctx.x;
+    b.raw[1] = h->ctx.anc;
+    b.raw[2] = h->d_mail;
+    for (int k = 0; k < 3; ++k) CU(cudaIpcGetMemHandle(&b.mem[k], b.raw[k]));
+    memset(blob_out, 0, APS_IPC_BLOB_BYTES);
+    memcpy(blob_out, &b, sizeof(b));
+    return APS_OK;
 }
+
 extern "C" int aps_ipc_import(aps_handle *h, const uint8_t *blobs) {
-    (void)h;
-    (void)blobs;
-    return fail(APS_ERR_COMM, "aps_ipc_import: multi-GPU sharding is not built yet");
+    if (!h || !blobs) return fail(APS_ERR_INVALID, "aps_ipc_import: null argument");
+    DevCtx &c = h->ctx;
+    if (c.world < 2) return fail(APS_ERR_INVALID, "aps_ipc_import: handle is not sharded (world_size == 1)");
+    CU(cudaSetDevice(h->cfg.device));
+    PeerTable pt;
+    memset(&pt, 0, sizeof(pt));
+    for (int r = 0; r < c.world; ++r) {
+        IpcBlob b;
+        memcpy(&b, blobs + (size_t)r * APS_IPC_BLOB_BYTES, sizeof(b));
+        if (b.magic != 0x4150534950433031ULL || b.rank != r)
+            return fail(APS_ERR_COMM, "aps_ipc_import: blob " + std::to_string(r) + " is not an aps_ipc_export blob of that rank");
+        void *p[3];
+        if (r == c.rank) {
+            p[0] = c.x; p[1] = c.anc; p[2] = h->d_mail;
+        } else if (b.pid == (long long)getpid()) {
+            // both ranks in one process: use the pointers directly (enable peer access across devices)
+            if (b.device != h->cfg.device) {
+                cudaError_t e = cudaDeviceEnablePeerAccess(b.device, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+                    return fail(APS_ERR_COMM, std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e));
+                cudaGetLastError();
+            }
+            for (int k = 0; k < 3; ++k) p[k] = b.raw[k];
+        } else {
+            for (int k = 0; k < 3; ++k) {
+                cudaError_t e = cudaIpcOpenMemHandle(&p[k], b.mem[k], cudaIpcMemLazyEnablePeerAccess);
+                if (e != cudaSuccess) return fail(APS_ERR_COMM, std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(e));
+                h->ipc_opened[h->n_ipc_opened++] = p[k];
+            }
+        }
+        pt.x[r] = (double *)p[0];
+        pt.anc[r] = (int32_t *)p[1];
+        pt.mail[r] = (MailSlot *)p[2];
+    }
+    CU(cudaMemcpy(h->d_peers, &pt, sizeof(pt), cudaMemcpyHostToDevice));
+    c.peers = h->d_peers;
+    if (h->graph_ready) {  // the captured graph holds the old context by value
+        cudaGraphExecDestroy(h->graph);
+        h->graph_ready = false;
+    }
+    h->comm_ready = true;
+    return APS_OK;
 }

@@ -23,6 +23,64 @@ typedef unsigned long long u64;
 #define APS_WARPS (APS_THREADS / 32)
 #define APS_K1_THREADS 256      // threads per block of the grid-stride kernels (propagate, maxima)
 
+// ---------------------------------------------------------------- multi-GPU sharding (one process per GPU)
+// Rank r owns the contiguous global slots [r Nl, (r+1) Nl). Peers' state / ancestor stores and a
+// small mailbox are mapped through CUDA IPC, so kernels address them with plain loads and stores
+// over NVLink. Three tiny exchanges per step run inside the kernels (no NCCL on the data path):
+//   kind 0  all-reduce(max) of the log-weight maximum       (last block of k_propagate)
+//   kind 1  all-gather of the integer weight totals           (last block of k_normalise)
+//   kind 2  barrier after the ancestor scatter                (last block of k_resample)
+// All combined quantities are integers, so every rank derives the identical plan.
+#define APS_MAX_RANKS 8
+struct MailSlot {
+    u64 seq;   // epoch * stride + step + 1 of the value currently in v[]
+    u64 v[3];
+};
+struct PeerTable {
+    double *x[APS_MAX_RANKS];
+    int32_t *anc[APS_MAX_RANKS];
+    MailSlot *mail[APS_MAX_RANKS];  // mail[r][kind * APS_MAX_RANKS + src]
+};
+
+__device__ __forceinline__ u64 ld_sys_u64(const u64 *p) {
+    u64 v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_sys_u64(u64 *p, u64 v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// Post v[0..2] of this rank to every peer's mailbox (slot `kind`), then wait until every rank's
+// value for sequence number `seq` has arrived in the local mailbox. Called by threads
+// 0..world-1 of one block; thread r handles peer r. Returns false on timeout.
+__device__ __forceinline__ bool mail_exchange(const PeerTable *pt, int rank, int world, int kind, u64 seq, const u64 *v,
+                                              u64 (*out)[3]) {
+    const int r = threadIdx.x;
+    bool ok = true;
+    if (r < world) {
+        MailSlot *dst = pt->mail[r] + kind * APS_MAX_RANKS + rank;
+        dst->v[0] = v[0];
+        dst->v[1] = v[1];
+        dst->v[2] = v[2];
+        __threadfence_system();
+        st_sys_u64(&dst->seq, seq);
+        const MailSlot *src = pt->mail[rank] + kind * APS_MAX_RANKS + r;
+        const long long t0 = clock64();
+        while (ld_sys_u64(&src->seq) < seq) {
+            if (clock64() - t0 > 6000000000LL) {  // ~3 s: a peer is gone; fail instead of hanging the GPU
+                ok = false;
+                break;
+            }
+        }
+        __threadfence_system();
+        out[r][0] = *(volatile const u64 *)&src->v[0];
+        out[r][1] = *(volatile const u64 *)&src->v[1];
+        out[r][2] = *(volatile const u64 *)&src->v[2];
+    }
+    return ok;
+}
+
 // per-decision-point accumulators, zeroed at sweep start (order-free integer atomics only)
 struct StepAcc {
     u64 max_enc;       // atomicMax of aps_encode_ordered(logw)
@@ -30,6 +88,8 @@ struct StepAcc {
     unsigned int bad;  // NaN seen
     unsigned int done_ctr;      // last-block detection, normalise kernel
     unsigned int sel_done_ctr;  // last-block detection, categorical kernel
+    unsigned int k1_done;       // last-block detection, propagate kernel (multi-GPU max exchange)
+    unsigned int k3_done;       // last-block detection, resample kernel (multi-GPU barrier)
     unsigned int pad;
 };
 

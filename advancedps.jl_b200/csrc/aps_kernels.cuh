@@ -19,6 +19,7 @@ struct SweepParams {
     u64 key;      // master seed of this sweep
     int has_ref;  // conditional sweep (PG / PGAS with a retained trajectory)
     int pad;
+    u64 epoch;    // sweeps run so far on this handle (sequence numbers of the multi-GPU mailbox)
 };
 
 struct DevCtx {
@@ -45,6 +46,10 @@ struct DevCtx {
     int pad;
     double ess_threshold;
     double logN;
+    long long Ng;          // global particle count (== N on one GPU); N is this rank's shard
+    long long slot0;       // global index of this rank's first slot
+    const PeerTable *peers; // device copy of the peer table, or null on one GPU
+    int rank, world;
     long long n_override;  // operator level: number of indices to draw (0: N, or N-1 with a reference)
     long long ctr_offset;  // operator level: Philox step counter = plan index + ctr_offset
 };
@@ -59,13 +64,13 @@ __global__ void k_init_sweep(const __grid_constant__ DevCtx c) {
         StepPlan p;
         p.M = 0.0;
         p.logZ = c.logN;
-        p.ess = (double)c.N;
-        p.Q = (u64)c.N << c.S;
+        p.ess = (double)c.Ng;
+        p.Q = (u64)c.Ng << c.S;
         p.R = 0;
         p.ratio = 0.0;
         p.roff = 0.0;
-        p.n = c.N - (c.sp->has_ref ? 1 : 0);
-        p.resampled = c.bare ? 1 : ((double)c.N <= c.ess_threshold * (double)c.N ? 1 : 0);
+        p.n = c.Ng - (c.sp->has_ref ? 1 : 0);
+        p.resampled = c.bare ? 1 : ((double)c.Ng <= c.ess_threshold * (double)c.Ng ? 1 : 0);
         p.err = 0;
         p.guard = 8;
         p.pad = 0;
@@ -96,10 +101,13 @@ __global__ void __launch_bounds__(APS_K1_THREADS) k_propagate(const __grid_const
     u64 bmax = 0;
     unsigned bad = 0;
     const long long npairs = (N + 1) >> 1;
+    const long long pair0 = c.slot0 >> 1;
+    const bool multi = c.world > 1;
+    const long long xoff = xp - c.x;  // slab offset, identical on every rank
     for (long long p = (long long)blockIdx.x * APS_K1_THREADS + threadIdx.x; p < npairs;
          p += (long long)gridDim.x * APS_K1_THREADS) {
         double z[2 * D];
-        aps_pair_normals<D>(key, (u64)p, (u64)t, z);
+        aps_pair_normals<D>(key, (u64)(pair0 + p), (u64)t, z);
         const long long i0 = 2 * p;
         int2 a2 = make_int2(0, 0);
         if (t > 1) a2 = *reinterpret_cast<const int2 *>(anc + i0);
@@ -121,10 +129,16 @@ __global__ void __launch_bounds__(APS_K1_THREADS) k_propagate(const __grid_const
                 } else if (t == 1) {
                     aps_prior_draw<D>(&c.md, z + h * D, x);
                 } else {
-                    const long long a = h ? a2.y : a2.x;
+                    long long a = h ? a2.y : a2.x;  // global parent index
+                    const double *xsrc = xp;
+                    if (multi) {  // the parent may live on a peer: read its state over NVLink
+                        const int owner = (int)((unsigned)a / (unsigned)N);
+                        a -= (long long)owner * N;
+                        xsrc = c.peers->x[owner] + xoff;
+                    }
                     double xpv[D];
 #pragma unroll
-                    for (int k = 0; k < D; ++k) xpv[k] = xp[(long long)k * NS + a];
+                    for (int k = 0; k < D; ++k) xpv[k] = xsrc[(long long)k * NS + a];
                     aps_trans_draw<D>(&c.md, xpv, z + h * D, x);
                 }
                 const double ll = aps_obs_logpdf<D, DY, OBS>(&c.md, x, y);
@@ -149,6 +163,28 @@ __global__ void __launch_bounds__(APS_K1_THREADS) k_propagate(const __grid_const
     if (threadIdx.x == 0) {
         if (bmax) atomicMax(&c.acc[t].max_enc, bmax);
         if (bad) atomicOr(&c.acc[t].bad, 1u);
+    }
+    if (multi) {
+        // last block: all-reduce(max) of the shard maxima through the peers' mailboxes
+        __shared__ unsigned s_last;
+        __shared__ u64 s_in[APS_MAX_RANKS][3];
+        if (threadIdx.x == 0) {
+            __threadfence();
+            s_last = atomicAdd(&c.acc[t].k1_done, 1u) == gridDim.x - 1 ? 1u : 0u;
+        }
+        __syncthreads();
+        if (!s_last) return;
+        __threadfence();
+        u64 v[3];
+        v[0] = atomicAdd(&c.acc[t].max_enc, 0ull);
+        v[1] = (u64)atomicOr(&c.acc[t].bad, 0u);
+        v[2] = 0;
+        const bool ok = mail_exchange(c.peers, c.rank, c.world, 0, c.sp->epoch * (u64)(c.T + 2) + (u64)t + 1, v, s_in);
+        if (threadIdx.x < c.world) {
+            atomicMax(&c.acc[t].max_enc, s_in[threadIdx.x][0]);
+            if (s_in[threadIdx.x][1]) atomicOr(&c.acc[t].bad, 1u);
+            if (!ok) c.st->err = APS_ERR_COMM;
+        }
     }
 }
 
@@ -179,10 +215,15 @@ __global__ void __launch_bounds__(APS_K1_THREADS) k_vector_max(const double *__r
 // One tile of APS_TILE particles per block: q_i = floor(exp(logw_i - M) 2^S), tile totals of q,
 // (q >> Hs) and (q >> Hs)^2. The last block to finish scans the tile totals and writes the plan
 // of decision point s: logZ, ESS, the resampling decision, the systematic offset, the evidence.
+// K2 is latency-bound at the particle counts of interest (one exp per particle), so it spreads a
+// tile over APS_K2_THREADS = 512 threads (4 particles each) instead of the 128 of the resampler.
+#define APS_K2_THREADS 512
+#define APS_K2_IPT (APS_TILE / APS_K2_THREADS)
+#define APS_K2_WARPS (APS_K2_THREADS / 32)
 template <int INPUT>
-__global__ void __launch_bounds__(APS_THREADS) k_normalise(const __grid_constant__ DevCtx c, const double *__restrict__ in,
+__global__ void __launch_bounds__(APS_K2_THREADS) k_normalise(const __grid_constant__ DevCtx c, const double *__restrict__ in,
                                                            const long long s) {
-    __shared__ u64 red[APS_THREADS / 32];
+    __shared__ u64 red[APS_K2_WARPS];
     __shared__ unsigned s_last;
     const long long N = c.N;
     const long long base = (long long)blockIdx.x * APS_TILE;
@@ -191,8 +232,8 @@ __global__ void __launch_bounds__(APS_THREADS) k_normalise(const __grid_constant
     const double scale = aps_pow2i(c.S);
     u64 s0 = 0, s1 = 0, s2 = 0;
 #pragma unroll
-    for (int r = 0; r < APS_IPT; ++r) {
-        const long long i = base + r * APS_THREADS + threadIdx.x;
+    for (int r = 0; r < APS_K2_IPT; ++r) {
+        const long long i = base + r * APS_K2_THREADS + threadIdx.x;
         if (i < N) {
             u64 qi;
             if (INPUT == IN_Q) {
@@ -210,9 +251,9 @@ __global__ void __launch_bounds__(APS_THREADS) k_normalise(const __grid_constant
             s2 += qs * qs;
         }
     }
-    s0 = block_sum_u64<APS_WARPS>(s0, red);
-    s1 = block_sum_u64<APS_WARPS>(s1, red);
-    s2 = block_sum_u64<APS_WARPS>(s2, red);
+    s0 = block_sum_u64<APS_K2_WARPS>(s0, red);
+    s1 = block_sum_u64<APS_K2_WARPS>(s1, red);
+    s2 = block_sum_u64<APS_K2_WARPS>(s2, red);
     if (threadIdx.x == 0) {
         c.tile_sum[blockIdx.x] = s0;
         c.tile_s1[blockIdx.x] = s1;
@@ -227,7 +268,7 @@ __global__ void __launch_bounds__(APS_THREADS) k_normalise(const __grid_constant
 
     // ---- last block: exclusive scan of the tile totals (each thread owns a contiguous chunk)
     const long long nt = c.num_tiles;
-    const long long per = (nt + APS_THREADS - 1) / APS_THREADS;
+    const long long per = (nt + APS_K2_THREADS - 1) / APS_K2_THREADS;
     const long long lo = (long long)threadIdx.x * per;
     const long long hi = lo + per < nt ? lo + per : nt;
     u64 a0 = 0, a1 = 0, a2 = 0;
@@ -237,13 +278,34 @@ __global__ void __launch_bounds__(APS_THREADS) k_normalise(const __grid_constant
         a2 += __ldcg(&c.tile_s2[k]);
     }
     u64 Q;
-    u64 run = block_excl_scan_u64<APS_WARPS>(a0, red, &Q);
+    u64 run = block_excl_scan_u64<APS_K2_WARPS>(a0, red, &Q);
+    u64 Q1 = block_sum_u64<APS_K2_WARPS>(a1, red);
+    u64 Q2 = block_sum_u64<APS_K2_WARPS>(a2, red);
+    if (c.world > 1) {
+        // all-gather of the shard totals; combined in rank order (integers: order is immaterial)
+        __shared__ u64 s_in[APS_MAX_RANKS][3];
+        __shared__ int s_ok;
+        u64 v[3] = {Q, Q1, Q2};
+        if (threadIdx.x == 0) s_ok = 1;
+        __syncthreads();
+        const bool ok = mail_exchange(c.peers, c.rank, c.world, 1, c.sp->epoch * (u64)(c.T + 2) + (u64)s + 1, v, s_in);
+        if (!ok) s_ok = 0;
+        __syncthreads();
+        u64 off = 0;
+        Q = 0, Q1 = 0, Q2 = 0;
+        for (int r = 0; r < c.world; ++r) {
+            if (r < c.rank) off += s_in[r][0];
+            Q += s_in[r][0];
+            Q1 += s_in[r][1];
+            Q2 += s_in[r][2];
+        }
+        run += off;
+        if (!s_ok && threadIdx.x == 0 && c.st) c.st->err = APS_ERR_COMM;
+    }
     for (long long k = lo; k < hi; ++k) {
         c.tile_prefix[k] = run;
         run += __ldcg(&c.tile_sum[k]);
     }
-    const u64 Q1 = block_sum_u64<APS_WARPS>(a1, red);
-    const u64 Q2 = block_sum_u64<APS_WARPS>(a2, red);
     if (threadIdx.x == 0) {
         StepPlan p;
         int err = 0;
@@ -259,8 +321,8 @@ __global__ void __launch_bounds__(APS_THREADS) k_normalise(const __grid_constant
         p.Q = Q;
         p.logZ = M + aps_log((double)Q * aps_pow2i(-c.S));
         p.ess = ((double)Q1 * (double)Q1) / (double)Q2;
-        p.resampled = c.bare ? 1 : (p.ess <= c.ess_threshold * (double)N ? 1 : 0);
-        p.n = c.n_override > 0 ? c.n_override : N - (c.sp->has_ref ? 1 : 0);
+        p.resampled = c.bare ? 1 : (p.ess <= c.ess_threshold * (double)c.Ng ? 1 : 0);
+        p.n = c.n_override > 0 ? c.n_override : c.Ng - (c.sp->has_ref ? 1 : 0);
         uint64_t w0, w1;
         aps_philox2x64(0, aps_ctr1((u64)(s + c.ctr_offset), APS_DOM_RESAMPLE, 0), c.sp->key, &w0, &w1);
         p.R = ceil_uq53(aps_u53(w0), Q);
@@ -336,9 +398,24 @@ __device__ __forceinline__ int strat_children_below(int F, u64 C, u64 Q, int n, 
 // accesses) turns the markers into parent ids, which leave as 128-bit global stores. Cost follows
 // the number of children, not the skew of the weights.
 //
+// destination of ancestor entries: child slot g (global index) -> address. On one GPU the local
+// slab; when sharded, the slab of the rank that owns slot g (a peer-mapped pointer: the ancestor
+// indices are scattered over NVLink with plain stores).
+struct AncDst {
+    int32_t *base;            // local slab
+    const PeerTable *peers;   // null on one GPU
+    long long slab_off;       // offset of the slab inside each rank's ancestor store
+    int nl;                   // slots per rank
+    __device__ __forceinline__ int32_t *at(int g) const {
+        if (!peers) return base + g;
+        const int owner = (int)((unsigned)g / (unsigned)nl);
+        return peers->anc[owner] + slab_off + (g - owner * nl);
+    }
+};
+
 // scan + store for the child slots [cb, cb + cnt) whose markers are already in own[]
-__device__ __forceinline__ void expand_scan_store(int cb, int cnt, int kA, int kB, int base,
-                                                  int32_t *__restrict__ anc_out, int *own, int *wmax) {
+__device__ __forceinline__ void expand_scan_store(int cb, int cnt, int kA, int kB, int base, const AncDst &dst, int *own,
+                                                  int *wmax) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int4 *own4 = reinterpret_cast<const int4 *>(own);
     const bool active = tid * APS_CPT < cnt;
@@ -384,13 +461,14 @@ __device__ __forceinline__ void expand_scan_store(int cb, int cnt, int kA, int k
             o.y = max(v[4 * m + 1], excl) + add;
             o.z = max(v[4 * m + 2], excl) + add;
             o.w = max(v[4 * m + 3], excl) + add;
+            int32_t *p = dst.at(g);  // 4-aligned groups never straddle two ranks (slots per rank % 32 == 0)
             if (g >= kA && g + 4 <= kB) {
-                *reinterpret_cast<int4 *>(anc_out + g) = o;
+                *reinterpret_cast<int4 *>(p) = o;
             } else {
-                if (g >= kA && g < kB) anc_out[g] = o.x;
-                if (g + 1 >= kA && g + 1 < kB) anc_out[g + 1] = o.y;
-                if (g + 2 >= kA && g + 2 < kB) anc_out[g + 2] = o.z;
-                if (g + 3 >= kA && g + 3 < kB) anc_out[g + 3] = o.w;
+                if (g >= kA && g < kB) p[0] = o.x;
+                if (g + 1 >= kA && g + 1 < kB) p[1] = o.y;
+                if (g + 2 >= kA && g + 2 < kB) p[2] = o.z;
+                if (g + 3 >= kA && g + 3 < kB) p[3] = o.w;
             }
         }
     }
@@ -405,8 +483,8 @@ __device__ __forceinline__ void zero_own(int *own) {
 
 // general (rare) path: any number of children, clipped chunk by chunk. khi: inclusive child
 // counts of this thread's parents, klo0: count below its first parent.
-__device__ __noinline__ void expand_tile_general(const int *khi, int klo0, int kA, int kB, int base,
-                                                 int32_t *__restrict__ anc_out, int *own, int *wmax) {
+__device__ __noinline__ void expand_tile_general(const int *khi, int klo0, int kA, int kB, int base, const AncDst &dst,
+                                                 int *own, int *wmax) {
     const int tid = threadIdx.x;
     for (int cb = kA & ~3; cb < kB; cb += APS_CAP) {
         const int cnt = (kB - cb) < APS_CAP ? (kB - cb) : APS_CAP;
@@ -421,7 +499,7 @@ __device__ __noinline__ void expand_tile_general(const int *khi, int klo0, int k
             klo = kh;
         }
         __syncthreads();
-        expand_scan_store(cb, cnt, kA, kB, base, anc_out, own, wmax);
+        expand_scan_store(cb, cnt, kA, kB, base, dst, own, wmax);
     }
 }
 
@@ -443,6 +521,23 @@ __device__ __forceinline__ int children_below_fast(u64 C, u64 Q, int n, double r
     int k = first_above_est(__fma_rn((double)C, ratio, -roff), n, guard, unsafe);
     if (KIND == APS_RESAMPLE_STRATIFIED) k = strat_children_below(k, C, Q, n, key, step);
     return k;
+}
+
+// Multi-GPU: the ancestor scatter of every rank must have landed before any rank propagates the
+// next step. Each block publishes its peer stores; the last block of the kernel trades a
+// sequence number with all peers and only then lets the kernel end.
+__device__ __forceinline__ void resample_barrier(const DevCtx &c, long long s) {
+    __shared__ unsigned s_last3;
+    __shared__ u64 s_in3[APS_MAX_RANKS][3];
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last3 = atomicAdd(&c.acc[s].k3_done, 1u) == gridDim.x - 1 ? 1u : 0u;
+    __syncthreads();
+    if (!s_last3) return;
+    __threadfence_system();
+    u64 v[3] = {0, 0, 0};
+    const bool ok = mail_exchange(c.peers, c.rank, c.world, 2, c.sp->epoch * (u64)(c.T + 2) + (u64)s + 1, v, s_in3);
+    if (!ok && c.st) c.st->err = APS_ERR_COMM;
 }
 
 // One tile of APS_TILE parents per block: reads their integer weights (8 B each), writes the
@@ -470,13 +565,20 @@ __global__ void __launch_bounds__(APS_THREADS, 8) k_resample(const __grid_consta
     const int tid = threadIdx.x;
     const long long base = (long long)blockIdx.x * APS_TILE;
 
+    AncDst dst;
+    dst.base = anc_out;
+    dst.peers = c.world > 1 ? c.peers : nullptr;
+    dst.slab_off = anc_out - c.anc;
+    dst.nl = (int)N;
+    const int gbase = (int)(c.slot0 + base);  // global index of the tile's first parent
     if (!pp->resampled || pp->err) {
         // update_keys! branch (src/container.jl:247): every particle continues, weights kept
 #pragma unroll
         for (int r = 0; r < APS_IPT; ++r) {
             const long long i = base + r * APS_THREADS + tid;
-            if (i < N) anc_out[i] = (int32_t)i;
+            if (i < N) anc_out[i] = (int32_t)(c.slot0 + i);
         }
+        if (c.world > 1) resample_barrier(c, s);
         return;
     }
     if (tid == 0) {
@@ -520,8 +622,9 @@ __global__ void __launch_bounds__(APS_THREADS, 8) k_resample(const __grid_consta
     const u64 excl = block_excl_scan_u64<APS_WARPS>(cum[APS_IPT - 1], red, &tile_total) + tprefix;  // syncs: own[] is zeroed
 
     // ---- child range of the tile and of this thread (every thread evaluates the three bounds itself)
+    const bool first_tile = blockIdx.x == 0 && c.slot0 == 0;  // K(C_{-1}) := 0 for the globally first parent
     bool unsafe = false;
-    const int kA = blockIdx.x == 0 ? 0 : children_below_fast<KIND>(tprefix, Q, n, ratio, roff, guard, key, step, &unsafe);
+    const int kA = first_tile ? 0 : children_below_fast<KIND>(tprefix, Q, n, ratio, roff, guard, key, step, &unsafe);
     const int kB = children_below_fast<KIND>(tprefix + tile_total, Q, n, ratio, roff, guard, key, step, &unsafe);
     int klo = tid == 0 ? kA : children_below_fast<KIND>(excl, Q, n, ratio, roff, guard, key, step, &unsafe);
     const int cb = kA & ~3;
@@ -538,11 +641,11 @@ __global__ void __launch_bounds__(APS_THREADS, 8) k_resample(const __grid_consta
     }
     const int slow = __syncthreads_or((unsafe || !single) ? 1 : 0);
     if (!slow) {
-        expand_scan_store(cb, kB - cb, kA, kB, (int)base, anc_out, own, wmax);
+        expand_scan_store(cb, kB - cb, kA, kB, gbase, dst, own, wmax);
     } else {
         // ---- retry (some estimate fell within the guard band of an integer, or the tile owns
         //      more children than one pass holds): same walk with exact fix-ups where needed
-        const int kAx = blockIdx.x == 0 ? 0 : children_below_checked<KIND>(tprefix, Q, R, n, ratio, roff, guard, key, step);
+        const int kAx = first_tile ? 0 : children_below_checked<KIND>(tprefix, Q, R, n, ratio, roff, guard, key, step);
         const int kBx = children_below_checked<KIND>(tprefix + tile_total, Q, R, n, ratio, roff, guard, key, step);
         int klx = tid == 0 ? kAx : children_below_checked<KIND>(excl, Q, R, n, ratio, roff, guard, key, step);
         const int cbx = kAx & ~3;
@@ -555,17 +658,18 @@ __global__ void __launch_bounds__(APS_THREADS, 8) k_resample(const __grid_consta
                 klx = k;
             }
             __syncthreads();
-            expand_scan_store(cbx, kBx - cbx, kAx, kBx, (int)base, anc_out, own, wmax);
+            expand_scan_store(cbx, kBx - cbx, kAx, kBx, gbase, dst, own, wmax);
         } else {
             int khi[APS_IPT];
             for (int r = 0; r < APS_IPT; ++r)
                 khi[r] = children_below_checked<KIND>(excl + cum[r], Q, R, n, ratio, roff, guard, key, step);
-            expand_tile_general(khi, klx, kAx, kBx, (int)base, anc_out, own, wmax);
+            expand_tile_general(khi, klx, kAx, kBx, gbase, dst, own, wmax);
         }
     }
 
     // reference particle keeps the last slot (src/container.jl:219-224); PGAS may overwrite it
-    if (blockIdx.x == gridDim.x - 1 && tid == 0 && n < N) anc_out[N - 1] = (int32_t)(N - 1);
+    if (blockIdx.x == gridDim.x - 1 && tid == 0 && n < c.Ng) anc_out[N - 1] = (int32_t)(N - 1);
+    if (c.world > 1) resample_barrier(c, s);
 }
 
 // ---------------------------------------------------------------- multinomial / residual resampling
@@ -702,7 +806,12 @@ __global__ void __launch_bounds__(APS_THREADS) k_expand_counts(const __grid_cons
     const int kB = kA + (int)tot;
 #pragma unroll
     for (int r = 0; r < APS_IPT; ++r) khi[r] += excl;
-    expand_tile_general(khi, excl, kA, kB, (int)base, anc_out, own, wmax);
+    AncDst dst;
+    dst.base = anc_out;
+    dst.peers = nullptr;
+    dst.slab_off = 0;
+    dst.nl = (int)a.N;
+    expand_tile_general(khi, excl, kA, kB, (int)base, dst, own, wmax);
     const long long n = a.plan->n;
     if (blockIdx.x == gridDim.x - 1 && tid == 0 && n < a.N && identity_if_not_resampled) anc_out[a.N - 1] = (int32_t)(a.N - 1);
 }
@@ -1038,9 +1147,10 @@ __global__ void __launch_bounds__(APS_THREADS) k_gather_final(const __grid_const
 
 // normalised weights W_i = q_i / Q (getweights, src/container.jl:95) or 1/N after a resample
 __global__ void __launch_bounds__(APS_THREADS) k_weights_out(const u64 *__restrict__ q, const StepPlan *p, long long N,
-                                                             int S, int force_uniform, double *__restrict__ out) {
+                                                             long long Ng, int S, int force_uniform,
+                                                             double *__restrict__ out) {
     const bool uni = force_uniform && p->resampled;
-    const double Qd = uni ? (double)((u64)N << S) : (double)p->Q;
+    const double Qd = uni ? (double)((u64)Ng << S) : (double)p->Q;
     const double qu = (double)(1ull << S);
     for (long long i = (long long)blockIdx.x * APS_THREADS + threadIdx.x; i < N;
          i += (long long)gridDim.x * APS_THREADS)
