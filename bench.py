@@ -25,7 +25,7 @@ DATA_KEY = 0xDA7A0002
 MASTER_SEED = 1234
 METRIC = "particle-steps/sec (N*T/s), LGSSM d=1 T=100 N=1e6"
 UNIT = "particle-steps/s"
-WORKLOAD = "configs[1]: linear-Gaussian SSM d=1 T=100 N=1e6 per GPU, SMC() systematic (bare: resample every step)"
+WORKLOAD = "configs[1]: linear-Gaussian SSM d=1 T=100 N=1e6 per GPU, SMC() systematic (bare: resample every step); N>1 GPUs = configs[4] shape (N = n_gpus x 1e6 in one sharded sweep)"
 
 
 def env_int(name, default):
@@ -48,7 +48,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
                  "-i", str(self.device)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
@@ -200,28 +200,32 @@ def main():
 
     model = models.linear_gaussian()
     Y = make_data()
-    cfg = _abi.make_config(model, N_PARTICLES, T_STEPS, device=local_rank)
-    h = _lib.Handle(cfg)
-    h.set_observations(Y)
+    if world == 1:
+        cfg = _abi.make_config(model, N_PARTICLES, T_STEPS, device=local_rank)
+        h = _lib.Handle(cfg)
+        h.set_observations(Y)
+    else:
+        # weak scaling: N = world x 1e6 particles in ONE sweep, sharded in contiguous blocks
+        from advancedps_b200 import distributed as D
+        h = D.create_sharded_handle(model, N_PARTICLES * world, T_STEPS, Y, device=local_rank)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
 
     # ---- value: device-resident inputs, CUDA events on the sweep's stream (inside the library)
-    for w in range(args.warmup):
-        h.sweep(MASTER_SEED + rank * 1000 + w)
     clocks = ClockSampler(local_rank)
+    clocks.start()  # sampled from the warm-up to the end of the e2e loop (the timed regions are ~0.1 s)
+    for w in range(args.warmup):
+        h.sweep(MASTER_SEED + w)
     barrier()
-    clocks.start()
     dev_ms, launches, logev = 0.0, 0, 0.0
     wall0 = time.perf_counter()
     for k in range(args.steps):
         flush.fill_(k & 0xFF)  # L2 flush between timed iterations (not timed)
         torch.cuda.synchronize()
-        logev = h.sweep(MASTER_SEED + rank * 1000 + k)
+        logev = h.sweep(MASTER_SEED + k)
         dev_ms += h.last_sweep_ms()
         launches += h.last_sweep_launches()
     barrier()
     wall = time.perf_counter() - wall0
-    clk = clocks.stop()
     t = torch.tensor([dev_ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -230,27 +234,37 @@ def main():
 
     # ---- e2e: the public API with host buffers; H2D of the observations and D2H of the
     #      SMCSample fields (weights + log-evidence) inside the timed region
-    tssm = S.TracedSSM(model, Y)
-    smc = S.SMC(N_PARTICLES, S.resample_systematic)
-    rng = np.random.default_rng(MASTER_SEED + rank)
-    del h
+    rng = np.random.default_rng(MASTER_SEED)
+    if world == 1:
+        tssm = S.TracedSSM(model, Y)
+        smc = S.SMC(N_PARTICLES, S.resample_systematic)
+        del h
+
+        def e2e_step():
+            return S.sample(rng, tssm, smc).weights
+    else:
+        def e2e_step():  # same calls sample() makes, on this rank's shard
+            h.set_observations(Y)
+            h.sweep(int(rng.integers(0, 2**63)))
+            return h.weights()
     for _ in range(args.warmup):
-        S.sample(rng, tssm, smc)
+        e2e_step()
     barrier()
     e0 = time.perf_counter()
     for _ in range(args.steps):
-        smp = S.sample(rng, tssm, smc)
+        wts = e2e_step()
     barrier()
     e2e_s = time.perf_counter() - e0
     t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = world * N_PARTICLES * T_STEPS * args.steps / float(t.item())
+    clk = clocks.stop()
     h2d = Y.nbytes + 16
-    d2h = smp.weights.nbytes + 24
+    d2h = wts.nbytes + 24
 
     # ---- roofline: per-launch CUDA events around every kernel of one sweep (same workload)
-    hp = S._handle_for(tssm, smc)
+    hp = S._handle_for(tssm, smc) if world == 1 else h
     hp.sweep_profiled(MASTER_SEED)
     _, cls_ms, cls_n = hp.sweep_profiled(MASTER_SEED)
     names = ["k_propagate", "k_normalise", "k_resample", "k_pgas"]
@@ -271,11 +285,13 @@ def main():
                 "kernels": kern}
     # the graded resample kernel in isolation: 2^25 particles (> L2), L2 flushed between launches
     n_iso = 1 << 25
-    avg_ms, min_ms = _lib.bench_resample(_abi.RESAMPLE_SYSTEMATIC, n_iso, iters=20, flush_l2=True)
-    iso = 12 * n_iso / (avg_ms * 1e-3) / 1e9
-    roofline["resample_isolated"] = {"n": n_iso, "avg_ms": avg_ms, "min_ms": min_ms, "achieved": iso,
-                                     "frac": iso / peak, "algorithmic_bytes_per_launch": 12 * n_iso,
-                                     "l2": "flushed between launches (512 MB memset)"}
+    if rank == 0:
+        avg_ms, min_ms = _lib.bench_resample(_abi.RESAMPLE_SYSTEMATIC, n_iso, iters=20, flush_l2=True)
+        iso = 12 * n_iso / (avg_ms * 1e-3) / 1e9
+        roofline["resample_isolated"] = {"n": n_iso, "avg_ms": avg_ms, "min_ms": min_ms, "achieved": iso,
+                                         "frac": iso / peak, "algorithmic_bytes_per_launch": 12 * n_iso,
+                                         "l2": "flushed between launches (512 MB memset)"}
+    barrier()
 
     if rank == 0:
         out = {
@@ -283,7 +299,7 @@ def main():
             "warmup": args.warmup, "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOAD, "n_particles_per_gpu": N_PARTICLES, "n_steps": T_STEPS,
-                       "parallelism": "single GPU" if world == 1 else f"{world} independent replicas (sharded sweep not built yet)",
+                       "parallelism": "single GPU" if world == 1 else f"one sweep of {world}e6 particles sharded over {world} GPUs (contiguous blocks; in-kernel NVLink mailbox exchanges + P2P ancestor scatter)",
                        "l2": "256 MB buffer written between timed sweeps; each sweep also streams 1.2 GB of state/ancestor history",
                        "timing": "CUDA events on the library's stream around the replayed CUDA graph, max over ranks"},
             "logevidence": logev, "wall_s": wall,
