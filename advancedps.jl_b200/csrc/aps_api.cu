@@ -3,6 +3,7 @@
 // points and the resample-kernel micro-benchmark. No torch types; plain pointers and sizes.
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <unistd.h>
 #include <string.h>
 #include <math.h>
@@ -271,6 +272,7 @@ extern "C" int aps_create(const aps_config *cfg, aps_handle **out) {
     c.rank = cfg->rank;
     c.world = world;
     c.peers = nullptr;
+    c.dbg = getenv("APS_DEBUG_MULTI") ? atoi(getenv("APS_DEBUG_MULTI")) : 0;
     c.NS = (Nl + 31) & ~31LL;
     c.T = T;
     c.d = d;
@@ -514,6 +516,20 @@ static int sweep_impl(aps_handle *h, uint64_t master_seed, const double *ref_tra
                                       ? "aps_sweep: a peer rank did not answer within the exchange timeout"
                                       : "aps_sweep: particle weights could not be normalised (all -Inf or NaN log-weights)");
     *logevidence = h->h_st->logev;
+    if (c.dbg & 16) {
+        std::vector<StepAcc> acc((size_t)c.T + 2);
+        cudaMemcpy(acc.data(), c.acc, sizeof(StepAcc) * acc.size(), cudaMemcpyDeviceToHost);
+        double span = 0, gap = 0;
+        for (long long t = 1; t <= c.T; ++t) {
+            span += (double)(acc[t].t_last[0] - ~acc[t].t_first_neg[0]);
+            if (t > 1) gap += (double)(~acc[t].t_first_neg[0] - acc[t - 1].t_last[0]);
+        }
+        fprintf(stderr, "[aps rank %d] k_propagate first-block-start -> last-block-end: %.2f us avg; end(t-1) -> start(t): %.2f us avg\n",
+                c.rank, span / c.T * 1e-3, gap / (c.T - 1) * 1e-3);
+    }
+    if (getenv("APS_DEBUG_SPIN") && c.world > 1)
+        fprintf(stderr, "[aps rank %d] block-0 wait cycles per sweep: max-exchange %llu, totals %llu, scatter-done %llu (T=%lld)\n",
+                c.rank, h->h_st->spin[0], h->h_st->spin[1], h->h_st->spin[2], c.T);
     return APS_OK;
 }
 

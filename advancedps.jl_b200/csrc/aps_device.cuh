@@ -33,8 +33,7 @@ typedef unsigned long long u64;
 // All combined quantities are integers, so every rank derives the identical plan.
 #define APS_MAX_RANKS 8
 struct MailSlot {
-    u64 seq;   // epoch * stride + step + 1 of the value currently in v[]
-    u64 v[3];
+    ulonglong2 pair[4];   // .x = value, .y = sequence number (epoch * stride + step + 1)
 };
 struct PeerTable {
     double *x[APS_MAX_RANKS];
@@ -51,32 +50,50 @@ __device__ __forceinline__ void st_sys_u64(u64 *p, u64 v) {
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
-// Post v[0..2] of this rank to every peer's mailbox (slot `kind`), then wait until every rank's
-// value for sequence number `seq` has arrived in the local mailbox. Called by threads
-// 0..world-1 of one block; thread r handles peer r. Returns false on timeout.
-__device__ __forceinline__ bool mail_exchange(const PeerTable *pt, int rank, int world, int kind, u64 seq, const u64 *v,
-                                              u64 (*out)[3]) {
+// Exchanges are push + poll with no fences: a kernel's results are complete (and its peer stores
+// landed) when the NEXT kernel of the stream starts, so block 0 of the consumer kernel publishes
+// them to every rank's mailbox and all blocks of the consumer kernel, on every rank, spin on
+// their LOCAL mailbox until every rank's values for the expected sequence number are there.
+// Each value travels with its sequence number in one 16-byte store (one NVLink transaction), so
+// no ordering between separate stores is needed.
+__device__ __forceinline__ void st_pair_sys(ulonglong2 *p, u64 v, u64 seq) {
+    asm volatile("st.relaxed.sys.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(v), "l"(seq) : "memory");
+}
+__device__ __forceinline__ ulonglong2 ld_pair_sys(const ulonglong2 *p) {
+    ulonglong2 r;
+    asm volatile("ld.relaxed.sys.global.v2.u64 {%0, %1}, [%2];" : "=l"(r.x), "=l"(r.y) : "l"(p) : "memory");
+    return r;
+}
+// publish nv values of this rank (threads 0..world-1 of ONE block; thread r writes to rank r)
+__device__ __forceinline__ void mail_post(const PeerTable *pt, int rank, int world, int kind, u64 seq, const u64 *v,
+                                          int nv) {
+    const int r = threadIdx.x;
+    if (r < world) {
+        MailSlot *dst = pt->mail[r] + kind * APS_MAX_RANKS + rank;
+        for (int k = 0; k < nv; ++k) st_pair_sys(&dst->pair[k], v[k], seq);
+    }
+}
+// wait for every rank's nv values of sequence number `seq` (threads 0..world-1 of a block; thread
+// r reads slot r of the local mailbox into out[r]). Returns false on timeout (~3 s: a peer is gone).
+__device__ __forceinline__ bool mail_wait(const PeerTable *pt, int rank, int world, int kind, u64 seq, u64 (*out)[4],
+                                          int nv, unsigned long long *spin = nullptr) {
     const int r = threadIdx.x;
     bool ok = true;
     if (r < world) {
-        MailSlot *dst = pt->mail[r] + kind * APS_MAX_RANKS + rank;
-        dst->v[0] = v[0];
-        dst->v[1] = v[1];
-        dst->v[2] = v[2];
-        __threadfence_system();
-        st_sys_u64(&dst->seq, seq);
         const MailSlot *src = pt->mail[rank] + kind * APS_MAX_RANKS + r;
         const long long t0 = clock64();
-        while (ld_sys_u64(&src->seq) < seq) {
-            if (clock64() - t0 > 6000000000LL) {  // ~3 s: a peer is gone; fail instead of hanging the GPU
-                ok = false;
-                break;
+        for (int k = 0; k < nv; ++k) {
+            ulonglong2 pr = ld_pair_sys(&src->pair[k]);
+            while (pr.y < seq) {
+                if (clock64() - t0 > 6000000000LL) {
+                    ok = false;
+                    break;
+                }
+                pr = ld_pair_sys(&src->pair[k]);
             }
+            out[r][k] = pr.x;
         }
-        __threadfence_system();
-        out[r][0] = *(volatile const u64 *)&src->v[0];
-        out[r][1] = *(volatile const u64 *)&src->v[1];
-        out[r][2] = *(volatile const u64 *)&src->v[2];
+        if (spin && blockIdx.x == 0 && r == (rank + 1) % world) atomicAdd(&spin[kind], (unsigned long long)(clock64() - t0));
     }
     return ok;
 }
@@ -88,9 +105,10 @@ struct StepAcc {
     unsigned int bad;  // NaN seen
     unsigned int done_ctr;      // last-block detection, normalise kernel
     unsigned int sel_done_ctr;  // last-block detection, categorical kernel
-    unsigned int k1_done;       // last-block detection, propagate kernel (multi-GPU max exchange)
-    unsigned int k3_done;       // last-block detection, resample kernel (multi-GPU barrier)
-    unsigned int pad;
+    unsigned int pad0, pad1, pad2;
+    u64 tot[4];                 // sharded: this rank's integer totals (Q, Q1, Q2 | nan-flag) and the global max
+    u64 t_first_neg[3];         // diagnostics (APS_DEBUG_SPAN): ~globaltimer of the first block start per kernel
+    u64 t_last[3];              // globaltimer of the last block end per kernel
 };
 
 // per-decision-point plan, written by the last block of the normalise kernel
@@ -114,6 +132,7 @@ struct SweepState {
     int err;
     int pad;
     long long picked_slot;
+    unsigned long long spin[4];  // diagnostics: cycles block 0 spent waiting in each mailbox wait kind
 };
 
 // ---------------------------------------------------------------- warp / block primitives
@@ -255,3 +274,19 @@ __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, u
 __device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap *map, int x, int y) {
     asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(map), "r"(x), "r"(y) : "memory");
 }
+
+__device__ __forceinline__ u64 global_timer_ns() {
+    u64 t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+struct SpanProbe {  // first-block-start / last-block-end of a kernel, for diagnostics only
+    StepAcc *a;
+    int k;
+    __device__ __forceinline__ SpanProbe(StepAcc *acc, int kind, int enabled) : a(enabled ? acc : nullptr), k(kind) {
+        if (a && threadIdx.x == 0) atomicMax(&a->t_first_neg[k], ~global_timer_ns());
+    }
+    __device__ __forceinline__ void end() {
+        if (a && threadIdx.x == 0) atomicMax(&a->t_last[k], global_timer_ns());
+    }
+};

