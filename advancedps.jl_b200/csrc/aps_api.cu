@@ -77,11 +77,11 @@ static pgas_fn pick_pgas_select(int d) {
         default: return k_pgas_select<4>;
     }
 }
-static res_fn pick_resample(int kind) {
-    switch (kind) {
-        case APS_RESAMPLE_STRATIFIED: return k_resample<APS_RESAMPLE_STRATIFIED>;
-        default: return k_resample<APS_RESAMPLE_SYSTEMATIC>;
-    }
+static res_fn pick_resample(int kind, bool multi = false) {
+    if (multi) return kind == APS_RESAMPLE_STRATIFIED ? k_resample<APS_RESAMPLE_STRATIFIED, true>
+                                                      : k_resample<APS_RESAMPLE_SYSTEMATIC, true>;
+    return kind == APS_RESAMPLE_STRATIFIED ? k_resample<APS_RESAMPLE_STRATIFIED, false>
+                                           : k_resample<APS_RESAMPLE_SYSTEMATIC, false>;
 }
 
 // ------------------------------------------------------------------ TMA descriptor of the integer-weight array
@@ -118,8 +118,11 @@ static void prefer_max_smem(F f) {
 static int enable_k3_smem() {
     static bool done = false;
     if (done) return APS_OK;
-    prefer_max_smem(k_resample<APS_RESAMPLE_SYSTEMATIC>);
-    prefer_max_smem(k_resample<APS_RESAMPLE_STRATIFIED>);
+    for (int kind : {APS_RESAMPLE_SYSTEMATIC, APS_RESAMPLE_STRATIFIED})
+        for (int multi = 0; multi < 2; ++multi) {
+            prefer_max_smem(pick_resample(kind, multi != 0));
+            CU(cudaFuncSetAttribute(pick_resample(kind, multi != 0), cudaFuncAttributeMaxDynamicSharedMemorySize, APS_K3_DYN_SMEM));
+        }
     prefer_max_smem(k_normalise<IN_LOGW>);
     prefer_max_smem(k_normalise<IN_W>);
     prefer_max_smem(k_normalise<IN_Q>);
@@ -127,8 +130,6 @@ static int enable_k3_smem() {
     prefer_max_smem(k_to_one_based);
     prefer_max_smem(k_vector_max<IN_W>);
     prefer_max_smem(k_vector_max<IN_LOGW>);
-    CU(cudaFuncSetAttribute(k_resample<APS_RESAMPLE_SYSTEMATIC>, cudaFuncAttributeMaxDynamicSharedMemorySize, APS_K3_DYN_SMEM));
-    CU(cudaFuncSetAttribute(k_resample<APS_RESAMPLE_STRATIFIED>, cudaFuncAttributeMaxDynamicSharedMemorySize, APS_K3_DYN_SMEM));
     done = true;
     return APS_OK;
 }
@@ -174,7 +175,7 @@ struct aps_handle {
     void *ipc_opened[3 * APS_MAX_RANKS];
     int n_ipc_opened;
     bool comm_ready;
-    unsigned long long epoch;
+    unsigned long long epoch, pick_seq;
     float last_ms;
     long long last_launches, graph_nodes;
     CUtensorMap tmap_q;
@@ -236,10 +237,6 @@ extern "C" int aps_create(const aps_config *cfg, aps_handle **out) {
     if (world < 1 || world > APS_MAX_RANKS || cfg->rank < 0 || cfg->rank >= world)
         return fail(APS_ERR_INVALID, "aps_create: rank / world_size out of range (1..8 ranks)");
     if (world > 1) {
-        if (cfg->sampler != APS_SMC)
-            return fail(APS_ERR_INVALID, "aps_create: the sharded sweep supports SMC only (PG / PGAS: single GPU)");
-        if (cfg->resampler != APS_RESAMPLE_SYSTEMATIC && cfg->resampler != APS_RESAMPLE_STRATIFIED)
-            return fail(APS_ERR_INVALID, "aps_create: the sharded sweep supports systematic / stratified resampling only");
         if (N % ((long long)world * 32) != 0)
             return fail(APS_ERR_INVALID, "aps_create: n_particles must be a multiple of 32 * world_size");
     }
@@ -305,8 +302,8 @@ extern "C" int aps_create(const aps_config *cfg, aps_handle **out) {
     CUH(cudaMalloc(&h->d_Y, sizeof(double) * (size_t)T * c.dy));
     CUH(cudaMalloc(&h->d_scratch, sizeof(double) * (size_t)Nl * d));
     if (world > 1) {
-        CUH(cudaMalloc(&h->d_mail, sizeof(MailSlot) * 3 * APS_MAX_RANKS));
-        CUH(cudaMemset(h->d_mail, 0, sizeof(MailSlot) * 3 * APS_MAX_RANKS));
+        CUH(cudaMalloc(&h->d_mail, sizeof(MailSlot) * APS_MAIL_KINDS * APS_MAX_RANKS));
+        CUH(cudaMemset(h->d_mail, 0, sizeof(MailSlot) * APS_MAIL_KINDS * APS_MAX_RANKS));
         CUH(cudaMalloc(&h->d_peers, sizeof(PeerTable)));
     }
     if (cfg->resampler == APS_RESAMPLE_MULTINOMIAL || cfg->resampler == APS_RESAMPLE_RESIDUAL) {
@@ -331,7 +328,7 @@ extern "C" int aps_create(const aps_config *cfg, aps_handle **out) {
     c.sp = h->d_sp;
     h->f_prop = pick_propagate(cfg->model.obs_kind, d, cfg->model.dy);
     prefer_max_smem(h->f_prop);
-    h->f_res = pick_resample(cfg->resampler);
+    h->f_res = pick_resample(cfg->resampler, world > 1);
     h->f_pmax = pick_pgas_max(d);
     h->f_psel = pick_pgas_select(d);
     prefer_max_smem(h->f_pmax);
@@ -411,6 +408,7 @@ static long long enqueue_sweep(aps_handle *h, LaunchProf *prof = nullptr) {
         if (c.resampler == APS_RESAMPLE_SYSTEMATIC || c.resampler == APS_RESAMPLE_STRATIFIED) {
             APS_LAUNCH(2, h->f_res<<<gt, APS_THREADS, APS_K3_DYN_SMEM, st>>>(c, t, anc_slab(t), h->tmap_q));
         } else {
+            const bool multi = c.world > 1;
             MultiArgs a;
             memset(&a, 0, sizeof(a));
             a.cum = h->d_cum;
@@ -422,24 +420,41 @@ static long long enqueue_sweep(aps_handle *h, LaunchProf *prof = nullptr) {
             a.N = c.N;
             a.num_tiles = c.num_tiles;
             a.step = t;
+            // sharded: the plan of this decision point comes from the exchanged shard totals
+            if (multi) {
+                APS_LAUNCH(2, k_plan_multi<<<1, 32, 0, st>>>(c, t));
+                a.child_off = &c.acc[t].child_off;
+            }
             if (c.resampler == APS_RESAMPLE_MULTINOMIAL) {
                 a.qsrc = c.q;
                 a.wplan = c.plan + t;
                 a.n_draws = &c.plan[t].n;
+                if (multi) {
+                    a.range_lo = &c.acc[t].rank_off;
+                    a.range_len = &c.acc[t].tot[0];
+                }
                 cudaMemsetAsync(h->d_counts, 0, sizeof(int) * (size_t)c.N, st);
                 cudaMemsetAsync(h->d_tile_count, 0, sizeof(int) * (size_t)c.num_tiles, st);
             } else {
                 a.qsrc = h->d_rq;
                 a.wplan = c.plan + c.T + 1;
                 a.n_draws = &h->d_rs[t].n_rest;
+                if (multi) {
+                    a.range_lo = &h->d_rs[t].q_off;
+                    a.range_len = &h->d_rs[t].q_local;
+                }
                 APS_LAUNCH(2, k_residual_split<<<gt, APS_THREADS, 0, st>>>(a, c.q, h->d_rq, h->d_rs + t));
+                if (multi) APS_LAUNCH(2, k_residual_exchange<0><<<1, 32, 0, st>>>(c, t, c.plan + t, h->d_rs + t, c.plan + c.T + 1));
                 APS_LAUNCH(2, k_residual_weights<<<gt, APS_THREADS, 0, st>>>(a, h->d_rq, h->d_rs + t, c.tile_sum, c.tile_prefix,
                                                                            c.plan + c.T + 1, h->d_done2 + t, &c.st->err));
+                if (multi) APS_LAUNCH(2, k_residual_exchange<1><<<1, 32, 0, st>>>(c, t, c.plan + t, h->d_rs + t, c.plan + c.T + 1));
             }
             APS_LAUNCH(2, k_cumsum<<<gt, APS_THREADS, 0, st>>>(a));
-            APS_LAUNCH(2, k_multi_search<1><<<gp, APS_K1_THREADS, 0, st>>>(a, &h->d_sp->key));
-            APS_LAUNCH(2, k_scan_tile_counts<<<1, APS_THREADS, 0, st>>>(a, nullptr));
-            APS_LAUNCH(2, k_expand_counts<<<gt, APS_THREADS, 0, st>>>(a, anc_slab(t), 1));
+            // sharded: every rank makes all Ng draws and keeps those in its own weight range
+            const int gs = stride_grid((c.Ng + 1) / 2);
+            APS_LAUNCH(2, k_multi_search<1><<<gs, APS_K1_THREADS, 0, st>>>(a, &h->d_sp->key));
+            APS_LAUNCH(2, k_scan_tile_counts<<<1, APS_THREADS, 0, st>>>(a, nullptr, c, t));
+            APS_LAUNCH(2, k_expand_counts<<<gt, APS_THREADS, 0, st>>>(a, anc_slab(t), 1, c));
         }
         if (c.sampler == APS_PGAS && t >= 2 && t <= c.T - 1) {
             APS_LAUNCH(3, h->f_pmax<<<gp, APS_K1_THREADS, 0, st>>>(c, t, x_slab(t - 1), anc_slab(t - 1), anc_slab(t)));
@@ -551,9 +566,10 @@ extern "C" int aps_sweep_profiled(aps_handle *h, uint64_t master_seed, const dou
 extern "C" int aps_pick_trajectory(aps_handle *h, double *traj_out, int64_t *index_out) {
     NEED_SWEEP("aps_pick_trajectory");
     if (!h->cfg.keep_history) return fail(APS_ERR_INVALID, "aps_pick_trajectory: handle was created with keep_history = 0");
-    if (h->ctx.world > 1) return fail(APS_ERR_INVALID, "aps_pick_trajectory: not available on a sharded handle yet");
     const DevCtx &c = h->ctx;
-    k_pick<<<1, APS_THREADS, 0, h->stream>>>(c, c.T, c.T + 1, APS_DOM_PICK);
+    // sharded: a collective call -- every rank picks (the ranks exchange their candidates) and
+    // walks the genealogy through the peer-mapped stores, so each ends up with the trajectory
+    k_pick<<<1, APS_THREADS, 0, h->stream>>>(c, c.T, c.T + 1, APS_DOM_PICK, ++h->pick_seq);
     k_backtrace<<<1, 32, 0, h->stream>>>(c, -1, h->d_traj);
     CU(cudaMemcpyAsync(h->d_ref, h->d_traj, sizeof(double) * (size_t)c.T * c.d, cudaMemcpyDeviceToDevice, h->stream));
     CU(cudaMemcpyAsync(h->h_st, c.st, sizeof(SweepState), cudaMemcpyDeviceToHost, h->stream));
@@ -605,7 +621,6 @@ extern "C" int aps_get_final_states(aps_handle *h, double *x_out) {
     NEED_SWEEP("aps_get_final_states");
     if (!x_out) return fail(APS_ERR_INVALID, "aps_get_final_states: null output");
     const DevCtx &c = h->ctx;
-    if (c.world > 1) return fail(APS_ERR_INVALID, "aps_get_final_states: not available on a sharded handle yet");
     k_gather_final<<<stride_grid(c.N), APS_THREADS, 0, h->stream>>>(c, h->d_scratch);
     CU(cudaMemcpyAsync(x_out, h->d_scratch, sizeof(double) * (size_t)c.N * c.d, cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
@@ -619,8 +634,7 @@ extern "C" int aps_get_trajectory(aps_handle *h, int64_t slot, double *traj_out)
     if (!h->cfg.keep_history) return fail(APS_ERR_INVALID, "aps_get_trajectory: handle was created with keep_history = 0");
     const DevCtx &c = h->ctx;
     if (slot < 0 || slot >= c.N) return fail(APS_ERR_INVALID, "aps_get_trajectory: slot out of range");
-    if (c.world > 1) return fail(APS_ERR_INVALID, "aps_get_trajectory: not available on a sharded handle yet");
-    k_backtrace<<<1, 32, 0, h->stream>>>(c, slot, h->d_traj);
+    k_backtrace<<<1, 32, 0, h->stream>>>(c, c.slot0 + slot, h->d_traj);  // slot: index in this rank's shard
     CU(cudaMemcpyAsync(traj_out, h->d_traj, sizeof(double) * (size_t)c.T * c.d, cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     CU(cudaGetLastError());
@@ -859,14 +873,14 @@ extern "C" int aps_resample(int kind, const double *wts, int64_t m, int64_t n, u
             a.n_draws = &w.d_rs->n_rest;
             a.out_offset = &w.d_rs->n_det;
             k_residual_split<<<gt, APS_THREADS, 0, w.stream>>>(a, w.d_q, w.d_rq, w.d_rs);
-            k_scan_tile_counts<<<1, APS_THREADS, 0, w.stream>>>(a, nullptr);
-            k_expand_counts<<<gt, APS_THREADS, 0, w.stream>>>(a, w.d_idx32, 0);
+            k_scan_tile_counts<<<1, APS_THREADS, 0, w.stream>>>(a, nullptr, c, 0);
+            k_expand_counts<<<gt, APS_THREADS, 0, w.stream>>>(a, w.d_idx32, 0, c);
             a.wplan = w.plan2;
             k_residual_weights<<<gt, APS_THREADS, 0, w.stream>>>(a, w.d_rq, w.d_rs, w.tile_sum, w.tile_prefix, w.plan2,
                                                                 w.d_done2, w.d_err);
         }
         k_cumsum<<<gt, APS_THREADS, 0, w.stream>>>(a);
-        k_multi_search<0><<<stride_grid(n), APS_K1_THREADS, 0, w.stream>>>(a, &w.sp->key);
+        k_multi_search<0><<<stride_grid((n + 1) / 2), APS_K1_THREADS, 0, w.stream>>>(a, &w.sp->key);
     }
     if (kind == APS_RESAMPLE_RESIDUAL) {
         int herr = 0;
@@ -964,7 +978,7 @@ extern "C" int aps_randcat(const double *wts, int64_t n, uint64_t key, uint64_t 
     memset(&st0, 0, sizeof(st0));
     st0.picked_slot = -1;
     CU(cudaMemcpyAsync(w.st, &st0, sizeof(st0), cudaMemcpyHostToDevice, w.stream));
-    k_pick<<<1, APS_THREADS, 0, w.stream>>>(cc, 0, (long long)ctr, APS_DOM_RESAMPLE);
+    k_pick<<<1, APS_THREADS, 0, w.stream>>>(cc, 0, (long long)ctr, APS_DOM_RESAMPLE, 0);
     CU(cudaMemcpyAsync(&st0, w.st, sizeof(st0), cudaMemcpyDeviceToHost, w.stream));
     CU(cudaStreamSynchronize(w.stream));
     CU(cudaGetLastError());

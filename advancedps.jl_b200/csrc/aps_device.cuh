@@ -26,12 +26,19 @@ typedef unsigned long long u64;
 // ---------------------------------------------------------------- multi-GPU sharding (one process per GPU)
 // Rank r owns the contiguous global slots [r Nl, (r+1) Nl). Peers' state / ancestor stores and a
 // small mailbox are mapped through CUDA IPC, so kernels address them with plain loads and stores
-// over NVLink. Three tiny exchanges per step run inside the kernels (no NCCL on the data path):
-//   kind 0  all-reduce(max) of the log-weight maximum       (last block of k_propagate)
-//   kind 1  all-gather of the integer weight totals           (last block of k_normalise)
-//   kind 2  barrier after the ancestor scatter                (last block of k_resample)
+// over NVLink. A few tiny exchanges per step run inside the kernels (no NCCL on the data path):
+//   kind 0  all-reduce(max) of the log-weight maximum       (posted by k_normalise)
+//   kind 1  all-gather of the integer weight totals           (posted by k_resample / k_plan_multi)
+//   kind 2  barrier after the ancestor scatter                (posted by k_propagate)
+//   kind 3  multinomial / residual: offspring totals per rank (k_scan_tile_counts)
+//   kind 4  residual: deterministic copies per rank           (k_residual_exchange<0>)
+//   kind 5  residual: residual-weight totals per rank         (k_residual_exchange<1>)
+//   kind 6  PGAS: maximum of the ancestor log-weights         (k_pgas_select)
+//   kind 7  PGAS: ancestor-weight totals per rank             (last block of k_pgas_select)
+//   kind 8  final pick: candidate slot per rank               (k_pick)
 // All combined quantities are integers, so every rank derives the identical plan.
 #define APS_MAX_RANKS 8
+#define APS_MAIL_KINDS 9
 struct MailSlot {
     ulonglong2 pair[4];   // .x = value, .y = sequence number (epoch * stride + step + 1)
 };
@@ -107,6 +114,8 @@ struct StepAcc {
     unsigned int sel_done_ctr;  // last-block detection, categorical kernel
     unsigned int pad0, pad1, pad2;
     u64 tot[4];                 // sharded: this rank's integer totals (Q, Q1, Q2 | nan-flag) and the global max
+    u64 rank_off;               // sharded: weight total of the lower ranks at this decision point
+    long long child_off;        // sharded multinomial / residual: children owned by parents of lower ranks
     u64 t_first_neg[3];         // diagnostics (APS_DEBUG_SPAN): ~globaltimer of the first block start per kernel
     u64 t_last[3];              // globaltimer of the last block end per kernel
 };

@@ -108,10 +108,12 @@ __global__ void __launch_bounds__(APS_K1_THREADS) k_propagate(const __grid_const
     const bool multi = c.world > 1;
     const u64 seq0 = multi ? c.sp->epoch * (u64)(c.T + 2) : 0ull;
     const long long xoff = xp - c.x;  // slab offset, identical on every rank
-    if (multi && t > 1) {
+    if (multi) {
         // the ancestor scatter of step t-1 (peer stores from every rank) must have landed: this
         // rank's resample kernel is complete (stream order), so block 0 tells every rank, and
-        // every block waits until all ranks said so.
+        // every block waits until all ranks said so. At t = 1 the same exchange makes sure every
+        // rank has finished its previous sweep (and trajectory extraction) before any state
+        // slab is overwritten.
         __shared__ u64 s_w[APS_MAX_RANKS][4];
         const u64 v0 = 0;
         if (blockIdx.x == 0) mail_post(c.peers, c.rank, c.world, 2, seq0 + (u64)(t - 1) + 1, &v0, 1);
@@ -138,7 +140,7 @@ __global__ void __launch_bounds__(APS_K1_THREADS) k_propagate(const __grid_const
 #pragma unroll
             for (int k = 0; k < D; ++k) x[k] = 0.0;
             if (i < N) {
-                if (has_ref && i == N - 1) {
+                if (has_ref && c.slot0 + i == c.Ng - 1) {  // the reference keeps the globally last slot
 #pragma unroll
                     for (int k = 0; k < D; ++k) x[k] = c.ref[(t - 1) * D + k];
                 } else if (t == 1) {
@@ -365,6 +367,54 @@ __global__ void __launch_bounds__(APS_K2_THREADS) k_normalise(const __grid_const
     }
 }
 
+// ---------------------------------------------------------------- sharded: the plan from the shard totals
+// One block posts `nv` values (shared memory) of this rank under (kind, seq) and collects every
+// rank's values into out[r][k]. Returns false when a peer did not answer (timeout).
+__device__ __forceinline__ bool block_exchange(const DevCtx &c, int kind, u64 seq, const u64 *v, int nv, u64 (*out)[4]) {
+    __syncthreads();
+    mail_post(c.peers, c.rank, c.world, kind, seq, v, nv);
+    bool ok = true;
+    if (!(c.dbg & 1)) ok = mail_wait(c.peers, c.rank, c.world, kind, seq, out, nv, c.st ? c.st->spin : nullptr);
+    return __syncthreads_and(ok ? 1 : 0) != 0;
+}
+__device__ __forceinline__ u64 step_seq(const DevCtx &c, long long s) { return c.sp->epoch * (u64)(c.T + 2) + (u64)s + 1; }
+
+// thread 0 of a block: combine the shard totals of every rank (rank order; integers) into the
+// plan of decision point s -- identical on every rank -- and this rank's exclusive weight offset
+__device__ __forceinline__ void multi_plan(const DevCtx &c, long long s, const u64 (*s_t)[4], bool comm_ok, StepPlan *plan,
+                                           u64 *rank_off) {
+    u64 Q = 0, Q1 = 0, Q2 = 0, off = 0;
+    int bad = 0;
+    for (int r = 0; r < c.world; ++r) {
+        if (r < c.rank) off += s_t[r][0];
+        Q += s_t[r][0];
+        Q1 += s_t[r][1];
+        Q2 += s_t[r][2] & 0x7FFFFFFFFFFFFFFFULL;
+        bad |= (int)(s_t[r][2] >> 63);
+    }
+    const u64 menc = s_t[0][3];
+    int err = (bad || menc == 0) ? APS_ERR_WEIGHTS : 0;
+    if (!comm_ok) err = APS_ERR_COMM;
+    make_plan<IN_LOGW>(c, s, aps_decode_ordered(menc), Q, Q1, Q2, err, plan);
+    *rank_off = off;
+}
+
+// sharded multinomial / residual: one block exchanges the shard totals and records the plan and
+// this rank's weight offset in global memory for the kernels that follow
+__global__ void __launch_bounds__(32) k_plan_multi(const __grid_constant__ DevCtx c, const long long s) {
+    __shared__ u64 s_t[APS_MAX_RANKS][4];
+    __shared__ u64 s_v[4];
+    if (threadIdx.x < 4) s_v[threadIdx.x] = c.acc[s].tot[threadIdx.x];
+    const bool ok = block_exchange(c, 1, step_seq(c, s), s_v, 4, s_t);
+    if (threadIdx.x == 0) {
+        StepPlan p;
+        u64 off;
+        multi_plan(c, s, s_t, ok, &p, &off);
+        c.acc[s].rank_off = off;
+        record_plan(c, s, p);
+    }
+}
+
 // ---------------------------------------------------------------- K3: resample
 // K(C) = #{ children i in [0,n) : i Q + R_i <= C n }: the number of children whose threshold lies
 // at or below cumulative weight C. Parent j owns children [K(C_{j-1}), K(C_j)).
@@ -555,7 +605,7 @@ __device__ __forceinline__ int children_below_fast(u64 C, u64 Q, int n, double r
 // zero-filled by the hardware, so ragged tails need no special case.
 #define APS_TILE_BYTES (APS_TILE * 8)
 #define APS_K3_DYN_SMEM (APS_TILE_BYTES + APS_CAP * 4)
-template <int KIND>
+template <int KIND, bool MULTI>
 __global__ void __launch_bounds__(APS_THREADS, 8) k_resample(const __grid_constant__ DevCtx c, const long long s,
                                                              int32_t *__restrict__ anc_out,
                                                              const __grid_constant__ CUtensorMap tmap_q) {
@@ -570,7 +620,7 @@ __global__ void __launch_bounds__(APS_THREADS, 8) k_resample(const __grid_consta
     const int tid = threadIdx.x;
     const long long base = (long long)blockIdx.x * APS_TILE;
     u64 rank_off = 0;
-    if (c.world > 1) {
+    if (MULTI) {
         // sharded: combine the shard totals published by the normalise kernels of every rank
         // (rank order; integers) and derive the plan locally -- identical on every rank
         __shared__ StepPlan s_plan;
@@ -584,21 +634,13 @@ __global__ void __launch_bounds__(APS_THREADS, 8) k_resample(const __grid_consta
         if (c.dbg & 1) { if (tid < c.world) { s_t[tid][0] = 1ull << 50; s_t[tid][1] = 1ull << 30; s_t[tid][2] = 1ull << 40; s_t[tid][3] = c.acc[s].max_enc; } }
         __syncthreads();
         if (tid == 0) {
-            u64 Q = 0, Q1 = 0, Q2 = 0, off = 0;
-            int bad = 0;
-            for (int r = 0; r < c.world; ++r) {
-                if (r < c.rank) off += s_t[r][0];
-                Q += s_t[r][0];
-                Q1 += s_t[r][1];
-                Q2 += s_t[r][2] & 0x7FFFFFFFFFFFFFFFULL;
-                bad |= (int)(s_t[r][2] >> 63);
-            }
-            const u64 menc = s_t[0][3];
-            int err = (bad || menc == 0) ? APS_ERR_WEIGHTS : 0;
-            if (!s_okt) err = APS_ERR_COMM;
-            make_plan<IN_LOGW>(c, s, aps_decode_ordered(menc), Q, Q1, Q2, err, &s_plan);
+            u64 off;
+            multi_plan(c, s, s_t, s_okt != 0, &s_plan, &off);
             s_off = off;
-            if (blockIdx.x == 0) record_plan(c, s, s_plan);
+            if (blockIdx.x == 0) {
+                c.acc[s].rank_off = off;
+                record_plan(c, s, s_plan);
+            }
         }
         __syncthreads();
         pp = &s_plan;
@@ -607,7 +649,7 @@ __global__ void __launch_bounds__(APS_THREADS, 8) k_resample(const __grid_consta
 
     AncDst dst;
     dst.base = anc_out;
-    dst.peers = (c.world > 1 && !(c.dbg & 8)) ? c.peers : nullptr;
+    dst.peers = (MULTI && !(c.dbg & 8)) ? c.peers : nullptr;
     dst.slab_off = anc_out - c.anc;
     dst.nl = (int)N;
     const int gbase = (int)(c.slot0 + base);  // global index of the tile's first parent
@@ -707,7 +749,7 @@ __global__ void __launch_bounds__(APS_THREADS, 8) k_resample(const __grid_consta
     }
 
     // reference particle keeps the last slot (src/container.jl:219-224); PGAS may overwrite it
-    if (blockIdx.x == gridDim.x - 1 && tid == 0 && n < c.Ng) anc_out[N - 1] = (int32_t)(N - 1);
+    if (blockIdx.x == gridDim.x - 1 && tid == 0 && n < c.Ng && c.rank == c.world - 1) anc_out[N - 1] = (int32_t)(c.Ng - 1);
 }
 
 // ---------------------------------------------------------------- multinomial / residual resampling
@@ -733,6 +775,10 @@ struct MultiArgs {
     long long N;
     long long num_tiles;
     long long step;         // Philox step counter of the draws
+    // sharded sweep (null / zero on one GPU): every rank makes all draws and keeps those that fall
+    // into its own weight range [*range_lo, *range_lo + *range_len)
+    const u64 *range_lo, *range_len;
+    long long *child_off;   // out: children owned by parents of lower ranks (k_scan_tile_counts)
 };
 
 // inclusive cumulative sums of one tile of qsrc (thread-blocked, 16 per thread)
@@ -752,7 +798,8 @@ __global__ void __launch_bounds__(APS_THREADS) k_cumsum(const __grid_constant__ 
         if (base + r < a.N) a.cum[base + r] = excl + cum[r];
 }
 
-// one i.i.d. draw per thread: two-level binary search (tile prefix, then the tile's cumulative sums)
+// i.i.d. draws: draw i is word (i & 1) of Philox block i >> 1, so one thread makes two draws; each
+// is a two-level binary search (tile prefix, then the tile's cumulative sums)
 template <int TO_COUNTS>
 __global__ void __launch_bounds__(APS_K1_THREADS) k_multi_search(const __grid_constant__ MultiArgs a, const u64 *keyp) {
     if (!a.plan->resampled || a.plan->err) return;
@@ -760,45 +807,55 @@ __global__ void __launch_bounds__(APS_K1_THREADS) k_multi_search(const __grid_co
     const u64 Q = a.wplan->Q;
     const u64 key = *keyp;
     const long long off = a.out_offset ? *a.out_offset : 0;
-    for (long long i = (long long)blockIdx.x * APS_K1_THREADS + threadIdx.x; i < nd;
-         i += (long long)gridDim.x * APS_K1_THREADS) {
-        uint64_t w0, w1;
-        aps_philox2x64((u64)i, aps_ctr1((u64)a.step, APS_DOM_RESAMPLE, 0), key, &w0, &w1);
-        const u64 tau = floor_uq53(aps_u53(w0), Q);
-        // last tile whose exclusive prefix is <= tau
-        long long lo = 0, hi = a.num_tiles - 1;
-        while (lo < hi) {
-            const long long mid = (lo + hi + 1) >> 1;
-            if (a.tile_prefix[mid] <= tau) lo = mid;
-            else hi = mid - 1;
-        }
-        const long long tile = lo;
-        long long jl = tile * APS_TILE, jh = jl + APS_TILE < a.N ? jl + APS_TILE : a.N;
-        --jh;  // first j in [jl, jh] with cum[j] > tau (exists unless trailing zero weights)
-        while (jl < jh) {
-            const long long mid = (jl + jh) >> 1;
-            if (a.cum[mid] > tau) jh = mid;
-            else jl = mid + 1;
-        }
-        if (TO_COUNTS) {
-            // warp-aggregated histogram: lanes that drew the same parent issue one atomic
-            const unsigned act = __activemask();
-            const unsigned same = __match_any_sync(act, (int)jl);
-            if ((int)(__ffs(same) - 1) == (int)(threadIdx.x & 31)) {
-                atomicAdd(&a.counts[jl], __popc(same));
+    const u64 lo_w = a.range_lo ? *a.range_lo : 0ull;
+    const u64 len_w = a.range_len ? *a.range_len : Q;
+    const long long npairs = (nd + 1) >> 1;
+    for (long long p = (long long)blockIdx.x * APS_K1_THREADS + threadIdx.x; p < npairs;
+         p += (long long)gridDim.x * APS_K1_THREADS) {
+        uint64_t w[2];
+        aps_philox2x64((u64)p, aps_ctr1((u64)a.step, APS_DOM_RESAMPLE, 0), key, &w[0], &w[1]);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const long long i = 2 * p + h;
+            const u64 tau = floor_uq53(aps_u53(w[h]), Q) - lo_w;  // relative to this rank's weight range
+            if (i >= nd || tau >= len_w) continue;                // (unsigned: also rejects tau below the range)
+            // last tile whose exclusive prefix is <= tau
+            long long lo = 0, hi = a.num_tiles - 1;
+            while (lo < hi) {
+                const long long mid = (lo + hi + 1) >> 1;
+                if (a.tile_prefix[mid] <= tau) lo = mid;
+                else hi = mid - 1;
             }
-            const unsigned samet = __match_any_sync(act, (int)tile);
-            if ((int)(__ffs(samet) - 1) == (int)(threadIdx.x & 31)) atomicAdd(&a.tile_count[tile], __popc(samet));
-        } else {
-            a.out32[off + i] = (int32_t)jl;
+            const long long tile = lo;
+            long long jl = tile * APS_TILE, jh = jl + APS_TILE < a.N ? jl + APS_TILE : a.N;
+            --jh;  // first j in [jl, jh] with cum[j] > tau (exists unless trailing zero weights)
+            while (jl < jh) {
+                const long long mid = (jl + jh) >> 1;
+                if (a.cum[mid] > tau) jh = mid;
+                else jl = mid + 1;
+            }
+            if (TO_COUNTS) {
+                // warp-aggregated histogram: lanes that drew the same parent issue one atomic
+                const unsigned act = __activemask();
+                const unsigned same = __match_any_sync(act, (int)jl);
+                if ((int)(__ffs(same) - 1) == (int)(threadIdx.x & 31)) atomicAdd(&a.counts[jl], __popc(same));
+                const unsigned samet = __match_any_sync(act, (int)tile);
+                if ((int)(__ffs(samet) - 1) == (int)(threadIdx.x & 31)) atomicAdd(&a.tile_count[tile], __popc(samet));
+            } else {
+                a.out32[off + i] = (int32_t)jl;
+            }
         }
     }
 }
 
-// exclusive scan of the per-tile offspring counts (one block)
-__global__ void __launch_bounds__(APS_THREADS) k_scan_tile_counts(const __grid_constant__ MultiArgs a, long long *total_out) {
+// exclusive scan of the per-tile offspring counts (one block). Sharded: the ranks exchange their
+// offspring totals; the children of this rank's parents start after those of the lower ranks.
+__global__ void __launch_bounds__(APS_THREADS) k_scan_tile_counts(const __grid_constant__ MultiArgs a, long long *total_out,
+                                                                  const __grid_constant__ DevCtx c, const long long s) {
     __shared__ u64 red[APS_WARPS];
-    if (!a.plan->resampled || a.plan->err) return;
+    __shared__ u64 s_v[1];
+    __shared__ u64 s_t[APS_MAX_RANKS][4];
+    if (!a.plan->resampled || a.plan->err) return;  // the plan is identical on every rank
     const long long nt = a.num_tiles;
     const long long per = (nt + APS_THREADS - 1) / APS_THREADS;
     const long long lo = (long long)threadIdx.x * per;
@@ -812,22 +869,36 @@ __global__ void __launch_bounds__(APS_THREADS) k_scan_tile_counts(const __grid_c
         run += (u64)a.tile_count[k];
     }
     if (threadIdx.x == 0 && total_out) *total_out = (long long)tot;
+    if (a.child_off) {
+        if (threadIdx.x == 0) s_v[0] = tot;
+        const bool ok = block_exchange(c, 3, step_seq(c, s), s_v, 1, s_t);
+        if (threadIdx.x == 0) {
+            u64 off = 0;
+            for (int r = 0; r < c.rank; ++r) off += s_t[r][0];
+            *a.child_off = (long long)off;
+            if (!ok) c.st->err = APS_ERR_COMM;
+        }
+    }
 }
 
-// offspring counts -> sorted ancestor indices (same expand machinery as k_resample)
+// offspring counts -> sorted ancestor indices (same expand machinery as k_resample). Sharded:
+// parent ids and child slots are global, children are scattered to the rank that owns their slot.
 __global__ void __launch_bounds__(APS_THREADS) k_expand_counts(const __grid_constant__ MultiArgs a, int32_t *__restrict__ anc_out,
-                                                               const int identity_if_not_resampled) {
+                                                               const int identity_if_not_resampled,
+                                                               const __grid_constant__ DevCtx c) {
     __shared__ u64 red[APS_WARPS];
     __shared__ __align__(16) int own[APS_CAP];
     __shared__ int wmax[APS_WARPS];
     const int tid = threadIdx.x;
     const long long base = (long long)blockIdx.x * APS_TILE;
+    const bool multi = a.child_off != nullptr;
+    const long long slot0 = multi ? c.slot0 : 0;
     if (!a.plan->resampled || a.plan->err) {
         if (identity_if_not_resampled) {
 #pragma unroll
             for (int r = 0; r < APS_IPT; ++r) {
                 const long long i = base + r * APS_THREADS + tid;
-                if (i < a.N) anc_out[i] = (int32_t)i;
+                if (i < a.N) anc_out[i] = (int32_t)(slot0 + i);
             }
         }
         return;
@@ -839,28 +910,33 @@ __global__ void __launch_bounds__(APS_THREADS) k_expand_counts(const __grid_cons
 #pragma unroll
     for (int r = 1; r < APS_IPT; ++r) khi[r] += khi[r - 1];
     u64 tot;
-    const int kA = a.tile_cprefix[blockIdx.x];
+    const int kA = a.tile_cprefix[blockIdx.x] + (multi ? (int)*a.child_off : 0);
     const int excl = (int)block_excl_scan_u64<APS_WARPS>((u64)khi[APS_IPT - 1], red, &tot) + kA;
     const int kB = kA + (int)tot;
 #pragma unroll
     for (int r = 0; r < APS_IPT; ++r) khi[r] += excl;
     AncDst dst;
     dst.base = anc_out;
-    dst.peers = nullptr;
-    dst.slab_off = 0;
+    dst.peers = (multi && !(c.dbg & 8)) ? c.peers : nullptr;
+    dst.slab_off = multi ? anc_out - c.anc : 0;
     dst.nl = (int)a.N;
-    expand_tile_general(khi, excl, kA, kB, (int)base, dst, own, wmax);
+    expand_tile_general(khi, excl, kA, kB, (int)(slot0 + base), dst, own, wmax);
     const long long n = a.plan->n;
-    if (blockIdx.x == gridDim.x - 1 && tid == 0 && n < a.N && identity_if_not_resampled) anc_out[a.N - 1] = (int32_t)(a.N - 1);
+    if (identity_if_not_resampled && blockIdx.x == gridDim.x - 1 && tid == 0) {  // reference particle: globally last slot
+        if (!multi && n < a.N) anc_out[a.N - 1] = (int32_t)(a.N - 1);
+        if (multi && n < c.Ng && c.rank == c.world - 1) anc_out[a.N - 1] = (int32_t)(c.Ng - 1);
+    }
 }
 
 // residual stage 1: deterministic copies d_j = floor(n q_j / Q) and raw residuals n q_j - d_j Q
 struct ResidualState {
-    u64 sum_d;         // total deterministic copies (atomic)
-    long long n_rest;  // Rc = n - sum_d
-    long long n_det;   // sum_d as a signed count (output offset of the residual draws)
+    u64 sum_d;         // deterministic copies of this rank's parents (atomic)
+    long long n_rest;  // Rc = n - (deterministic copies of all ranks)
+    long long n_det;   // deterministic copies as a signed count (output offset of the residual draws)
     int shift;         // ceil_log2(Rc + 1)
     unsigned done_ctr;
+    u64 q_local;       // sharded: residual-weight total of this rank ...
+    u64 q_off;         // ... and of the lower ranks
 };
 
 __global__ void __launch_bounds__(APS_THREADS) k_residual_split(const __grid_constant__ MultiArgs a, const u64 *__restrict__ q,
@@ -895,7 +971,7 @@ __global__ void __launch_bounds__(APS_THREADS) k_residual_split(const __grid_con
         atomicAdd(&rs->sum_d, sd);
         __threadfence();
         const unsigned ticket = atomicAdd(&rs->done_ctr, 1u);
-        if (ticket == gridDim.x - 1) {
+        if (ticket == gridDim.x - 1 && !a.child_off) {  // sharded: k_residual_exchange<0> combines the ranks
             __threadfence();
             const u64 tot = atomicAdd(&rs->sum_d, 0ull);
             const long long rc = (long long)n - (long long)tot;
@@ -949,8 +1025,44 @@ __global__ void __launch_bounds__(APS_THREADS) k_residual_weights(const __grid_c
         run += __ldcg(&tile_sum[k]);
     }
     if (threadIdx.x == 0) {
-        wplan->Q = tot;
-        if (tot == 0 && err_out) *err_out = APS_ERR_WEIGHTS;
+        if (a.child_off) {  // sharded: k_residual_exchange<1> combines the ranks
+            const_cast<ResidualState *>(rs)->q_local = tot;
+        } else {
+            wplan->Q = tot;
+            if (tot == 0 && err_out) *err_out = APS_ERR_WEIGHTS;
+        }
+    }
+}
+
+// sharded residual resampling, one block. STAGE 0: exchange the deterministic-copy counts -> the
+// number of residual draws and the residual shift. STAGE 1: exchange the residual-weight totals
+// -> their global total (wplan->Q) and this rank's offset.
+template <int STAGE>
+__global__ void __launch_bounds__(32) k_residual_exchange(const __grid_constant__ DevCtx c, const long long s,
+                                                          const StepPlan *plan, ResidualState *rs, StepPlan *wplan) {
+    __shared__ u64 s_v[1];
+    __shared__ u64 s_t[APS_MAX_RANKS][4];
+    if (!plan->resampled || plan->err) return;
+    if (STAGE == 1 && rs->n_rest <= 0) return;  // identical on every rank
+    if (threadIdx.x == 0) s_v[0] = STAGE == 0 ? rs->sum_d : rs->q_local;
+    const bool ok = block_exchange(c, 4 + STAGE, step_seq(c, s), s_v, 1, s_t);
+    if (threadIdx.x == 0) {
+        u64 tot = 0, off = 0;
+        for (int r = 0; r < c.world; ++r) {
+            if (r < c.rank) off += s_t[r][0];
+            tot += s_t[r][0];
+        }
+        if (STAGE == 0) {
+            const long long rc = plan->n - (long long)tot;
+            rs->n_rest = rc;
+            rs->n_det = (long long)tot;
+            rs->shift = aps_ceil_log2((uint64_t)rc + 1);
+        } else {
+            wplan->Q = tot;
+            rs->q_off = off;
+            if (tot == 0) c.st->err = APS_ERR_WEIGHTS;
+        }
+        if (!ok) c.st->err = APS_ERR_COMM;
     }
 }
 
@@ -961,11 +1073,17 @@ template <int D>
 __device__ __forceinline__ double pgas_logweight(const DevCtx &c, long long s, long long i,
                                                  const double *__restrict__ xpp, const int32_t *__restrict__ anc_cur) {
     const long long N = c.NS;
-    const long long a = anc_cur[i];
+    long long a = anc_cur[i];  // global index of the parent in set s-1
+    const double *xsrc = xpp;
+    if (c.world > 1) {  // the parent may live on a peer: read its state over NVLink
+        const int owner = (int)((unsigned)a / (unsigned)c.N);
+        a -= (long long)owner * c.N;
+        xsrc = c.peers->x[owner] + (xpp - c.x);
+    }
     double xp[D], xr[D];
 #pragma unroll
     for (int k = 0; k < D; ++k) {
-        xp[k] = xpp[(long long)k * N + a];
+        xp[k] = xsrc[(long long)k * N + a];
         xr[k] = c.ref[(s - 1) * D + k];                                   // X_ref[c-1], c = s+1
     }
     return aps_trans_logpdf<D>(&c.md, xp, xr) + c.logw[i];
@@ -1026,6 +1144,8 @@ __device__ __forceinline__ int tile_find_first_above(const u64 *w8, u64 prefix, 
 
 // PGAS: tile totals of the quantised ancestor weights; the last block locates the drawn tile,
 // rescans it and rewires the reference's ancestor pointer (the splice of src/pgas.jl:125-127).
+// Sharded: the ranks exchange the maximum (every block) and their weight totals (last block);
+// the rank whose weight range holds the draw writes the ancestor into the last rank's store.
 template <int D>
 __global__ void __launch_bounds__(APS_THREADS) k_pgas_select(const __grid_constant__ DevCtx c, const long long s,
                                                              const double *__restrict__ xpp,
@@ -1035,10 +1155,32 @@ __global__ void __launch_bounds__(APS_THREADS) k_pgas_select(const __grid_consta
     __shared__ long long s_tile;
     __shared__ u64 s_pref, s_tau;
     __shared__ int s_found;
-    if (!pgas_active(c, s)) return;
+    __shared__ u64 s_m[APS_MAX_RANKS][4];
+    __shared__ u64 s_v[2];
+    if (!pgas_active(c, s)) return;  // identical on every rank
     const long long N = c.N;
+    const bool multi = c.world > 1;
     StepAcc *acc = &c.acc[s];
-    const double M = aps_decode_ordered(acc->sel_max_enc);
+    u64 menc = acc->sel_max_enc;
+    unsigned bad_in = acc->bad & 2u;
+    if (multi) {  // all-reduce(max) of the ancestor log-weights: k_pgas_max of this rank is complete
+        if (threadIdx.x == 0) {
+            s_v[0] = menc;
+            s_v[1] = bad_in;
+        }
+        __syncthreads();
+        if (blockIdx.x == 0) mail_post(c.peers, c.rank, c.world, 6, step_seq(c, s), s_v, 2);
+        bool ok = true;
+        if (!(c.dbg & 1)) ok = mail_wait(c.peers, c.rank, c.world, 6, step_seq(c, s), s_m, 2, nullptr);
+        if (!__syncthreads_and(ok ? 1 : 0) && threadIdx.x == 0) c.st->err = APS_ERR_COMM;
+        menc = 0;
+        for (int r = 0; r < c.world; ++r) {
+            menc = s_m[r][0] > menc ? s_m[r][0] : menc;
+            bad_in |= (unsigned)s_m[r][1];
+        }
+        __syncthreads();
+    }
+    const double M = aps_decode_ordered(menc);
     const double scale = aps_pow2i(c.S);
     const long long base = (long long)blockIdx.x * APS_TILE;
     u64 s0 = 0;
@@ -1067,19 +1209,30 @@ __global__ void __launch_bounds__(APS_THREADS) k_pgas_select(const __grid_consta
     const long long hi = lo + per < nt ? lo + per : nt;
     u64 a0 = 0;
     for (long long k = lo; k < hi; ++k) a0 += __ldcg(&c.tile_s1[k]);
-    u64 Qs;
-    u64 run = block_excl_scan_u64<APS_WARPS>(a0, red, &Qs);
+    u64 Qloc;
+    u64 run = block_excl_scan_u64<APS_WARPS>(a0, red, &Qloc);
+    u64 Qs = Qloc, off = 0;
+    if (multi) {  // all-gather of the ancestor-weight totals, combined in rank order
+        if (threadIdx.x == 0) s_v[0] = Qloc;
+        const bool ok = block_exchange(c, 7, step_seq(c, s), s_v, 1, s_m);
+        Qs = 0;
+        for (int r = 0; r < c.world; ++r) {
+            if (r < c.rank) off += s_m[r][0];
+            Qs += s_m[r][0];
+        }
+        if (!ok && threadIdx.x == 0) c.st->err = APS_ERR_COMM;
+    }
     if (threadIdx.x == 0) {
         s_tile = -1;
         uint64_t w0, w1;
         aps_philox2x64(0, aps_ctr1((u64)s, APS_DOM_PGAS, 0), c.sp->key, &w0, &w1);
-        s_tau = floor_uq53(aps_u53(w0), Qs);
+        s_tau = floor_uq53(aps_u53(w0), Qs) - off;  // relative to this rank's weight range
         const double Mv = M;
-        if (acc->bad & 2u || Qs == 0 || !(Mv == Mv) || Mv == aps_bits2d(0xFFF0000000000000ULL)) c.st->err = APS_ERR_WEIGHTS;
+        if (bad_in || Qs == 0 || !(Mv == Mv) || Mv == aps_bits2d(0xFFF0000000000000ULL)) c.st->err = APS_ERR_WEIGHTS;
     }
     __syncthreads();
     const u64 tau = s_tau;
-    if (Qs == 0) return;
+    if (Qs == 0 || tau >= Qloc) return;  // (unsigned: also rejects draws below this rank's range)
     for (long long k = lo; k < hi; ++k) {
         const u64 t = __ldcg(&c.tile_s1[k]);
         if (run <= tau && tau < run + t) {
@@ -1103,83 +1256,115 @@ __global__ void __launch_bounds__(APS_THREADS) k_pgas_select(const __grid_consta
     }
     const int f = tile_find_first_above(w8, s_pref, tau, red, &s_found);
     if (threadIdx.x == 0 && f >= 0) {
-        anc_out[N - 1] = (int32_t)(tile * APS_TILE + f);
+        // the reference particle is the globally last slot: last slot of the last rank's store
+        int32_t *dst = multi ? c.peers->anc[c.world - 1] + (anc_out - c.anc) + (N - 1) : anc_out + (N - 1);
+        *dst = (int32_t)(c.slot0 + tile * APS_TILE + f);
     }
 }
 
 // final pick over the weights of the final set: rand(pc.rng, pc) (src/container.jl:33-36).
-// One block. If the last decision point resampled, the weights are uniform.
+// One block. If the last decision point resampled, the weights are uniform. picked_slot is a
+// GLOBAL slot index. Sharded: every rank looks for the draw in its own weight range and the ranks
+// exchange their candidates (pick_seq: number of picks made on this handle so far).
 __global__ void __launch_bounds__(APS_THREADS) k_pick(const __grid_constant__ DevCtx c, const long long plan_idx,
-                                                      const long long step_ctr, const unsigned dom) {
+                                                      const long long step_ctr, const unsigned dom, const u64 pick_seq) {
     __shared__ u64 red[APS_THREADS / 32];
     __shared__ long long s_tile;
     __shared__ u64 s_pref;
     __shared__ int s_found;
+    __shared__ u64 s_v[1];
+    __shared__ u64 s_t[APS_MAX_RANKS][4];
     const long long N = c.N;
+    const bool multi = c.world > 1;
     const StepPlan &p = c.plan[plan_idx];
     uint64_t w0, w1;
     aps_philox2x64(0, aps_ctr1((u64)step_ctr, dom, 0), c.sp->key, &w0, &w1);
     const u64 U = aps_u53(w0);
     if (p.resampled) {
         if (threadIdx.x == 0) {
-            const u64 Q = (u64)N << c.S;
+            const u64 Q = (u64)c.Ng << c.S;
             long long slot = (long long)(floor_uq53(U, Q) >> c.S);
-            if (slot >= N) slot = N - 1;
+            if (slot >= c.Ng) slot = c.Ng - 1;
             c.st->picked_slot = slot;
         }
         return;
     }
-    const u64 tau = floor_uq53(U, p.Q);
+    const u64 off = multi ? c.acc[plan_idx].rank_off : 0ull;
+    const u64 Qloc = multi ? c.acc[plan_idx].tot[0] : p.Q;
+    const u64 tau = floor_uq53(U, p.Q) - off;  // relative to this rank's weight range
     const long long nt = c.num_tiles;
     if (threadIdx.x == 0) s_tile = -1;
     __syncthreads();
-    for (long long k = threadIdx.x; k < nt; k += APS_THREADS) {
-        const u64 pre = c.tile_prefix[k];
-        const u64 t = c.tile_sum[k];
-        if (pre <= tau && tau < pre + t) {
-            s_tile = k;
-            s_pref = pre;
+    if (tau < Qloc) {
+        for (long long k = threadIdx.x; k < nt; k += APS_THREADS) {
+            const u64 pre = c.tile_prefix[k];
+            const u64 t = c.tile_sum[k];
+            if (pre <= tau && tau < pre + t) {
+                s_tile = k;
+                s_pref = pre;
+            }
         }
     }
     __syncthreads();
     const long long tile = s_tile;
-    if (tile < 0) return;
-    u64 w8[APS_IPT];
+    long long cand = -1;
+    if (tile >= 0) {
+        u64 w8[APS_IPT];
 #pragma unroll
-    for (int r = 0; r < APS_IPT; ++r) {
-        const long long i = tile * APS_TILE + (long long)threadIdx.x * APS_IPT + r;
-        w8[r] = i < N ? c.q[i] : 0ull;
+        for (int r = 0; r < APS_IPT; ++r) {
+            const long long i = tile * APS_TILE + (long long)threadIdx.x * APS_IPT + r;
+            w8[r] = i < N ? c.q[i] : 0ull;
+        }
+        const int f = tile_find_first_above(w8, s_pref, tau, red, &s_found);
+        if (f >= 0) cand = c.slot0 + tile * APS_TILE + f;
     }
-    const int f = tile_find_first_above(w8, s_pref, tau, red, &s_found);
-    if (threadIdx.x == 0 && f >= 0) c.st->picked_slot = tile * APS_TILE + f;
+    if (multi) {
+        if (threadIdx.x == 0) s_v[0] = (u64)(cand + 1);
+        const bool ok = block_exchange(c, 8, pick_seq, s_v, 1, s_t);
+        cand = -1;
+        for (int r = 0; r < c.world; ++r)
+            if (s_t[r][0]) cand = (long long)s_t[r][0] - 1;
+        if (!ok) cand = -1;
+    }
+    if (threadIdx.x == 0 && cand >= 0) c.st->picked_slot = cand;
 }
 
-// trajectory of one final-set slot: T pointer hops through the ancestor store
+// state / ancestor of a GLOBAL slot index (sharded: through the owner's peer-mapped store)
+__device__ __forceinline__ double load_state(const DevCtx &c, long long slab, int k, long long g) {
+    const long long off = slab * (long long)c.d * c.NS + (long long)k * c.NS;
+    if (c.world == 1) return c.x[off + g];
+    const int owner = (int)(g / c.N);
+    return c.peers->x[owner][off + (g - (long long)owner * c.N)];
+}
+__device__ __forceinline__ long long load_anc(const DevCtx &c, long long slab, long long g) {
+    if (c.world == 1) return c.anc[slab * c.NS + g];
+    const int owner = (int)(g / c.N);
+    return c.peers->anc[owner][slab * c.NS + (g - (long long)owner * c.N)];
+}
+
+// trajectory of one final-set slot (global index): T pointer hops through the ancestor store
 __global__ void k_backtrace(const __grid_constant__ DevCtx c, const long long slot_in, double *__restrict__ traj) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    const long long N = c.N, T = c.T;
+    const long long T = c.T;
     const int D = c.d;
     const long long slot = slot_in >= 0 ? slot_in : c.st->picked_slot;
-    if (slot < 0 || slot >= N) return;
-    const long long NS = c.NS;
-    long long j = c.anc[(T % c.anc_slabs) * NS + slot];
+    if (slot < 0 || slot >= c.Ng) return;
+    long long j = load_anc(c, T % c.anc_slabs, slot);
     for (long long t = T; t >= 1; --t) {
-        const double *xt = c.x + ((t - 1) % c.x_slabs) * (long long)D * NS;
-        for (int k = 0; k < D; ++k) traj[(t - 1) * D + k] = xt[(long long)k * NS + j];
-        j = c.anc[((t - 1) % c.anc_slabs) * NS + j];
+        for (int k = 0; k < D; ++k) traj[(t - 1) * D + k] = load_state(c, (t - 1) % c.x_slabs, k, j);
+        if (t > 1) j = load_anc(c, (t - 1) % c.anc_slabs, j);
     }
 }
 
-// final particle set as N x d row-major: x_T[anc_{T+1}[i]]   (collect(pc), src/smc.jl:56)
+// final particle set (this rank's slots) as N x d row-major: x_T[anc_{T+1}[i]]   (collect(pc), src/smc.jl:56)
 __global__ void __launch_bounds__(APS_THREADS) k_gather_final(const __grid_constant__ DevCtx c, double *__restrict__ out) {
     const long long N = c.N, T = c.T;
     const int D = c.d;
     const int32_t *anc = c.anc + (T % c.anc_slabs) * c.NS;
-    const double *xt = c.x + ((T - 1) % c.x_slabs) * (long long)D * c.NS;
     for (long long i = (long long)blockIdx.x * APS_THREADS + threadIdx.x; i < N;
          i += (long long)gridDim.x * APS_THREADS) {
         const long long a = anc[i];
-        for (int k = 0; k < D; ++k) out[i * D + k] = xt[(long long)k * c.NS + a];
+        for (int k = 0; k < D; ++k) out[i * D + k] = load_state(c, (T - 1) % c.x_slabs, k, a);
     }
 }
 

@@ -25,8 +25,11 @@ def combine_totals(totals, rank):
 
 
 def create_sharded_handle(model, n_global, n_steps, Y, resampler=_abi.RESAMPLE_SYSTEMATIC,
-                          ess_threshold=float("nan"), keep_history=True, device=None, group=None):
-    """Build this rank's handle of a sharded SMC sweep and attach the peers (collective call)."""
+                          ess_threshold=float("nan"), keep_history=True, device=None, group=None,
+                          sampler=_abi.SAMPLER_SMC):
+    """Build this rank's handle of a sharded SMC / PG / PGAS sweep and attach the peers (collective
+    call). ``sweep`` and ``pick_trajectory`` on the returned handle are collective too: every rank
+    calls them with the same arguments."""
     import torch
     import torch.distributed as dist
 
@@ -34,7 +37,7 @@ def create_sharded_handle(model, n_global, n_steps, Y, resampler=_abi.RESAMPLE_S
     if device is None:
         device = torch.cuda.current_device()
     shard_bounds(n_global, world, rank)
-    cfg = _abi.make_config(model, n_global, n_steps, sampler=_abi.SAMPLER_SMC, resampler=resampler,
+    cfg = _abi.make_config(model, n_global, n_steps, sampler=sampler, resampler=resampler,
                            ess_threshold=ess_threshold, keep_history=keep_history, device=device,
                            rank=rank, world_size=world)
     h = _lib.Handle(cfg)

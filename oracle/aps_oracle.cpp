@@ -290,6 +290,13 @@ static uint64_t draw_u53(uint64_t key, uint64_t idx, uint64_t step, uint32_t dom
     aps_philox2x64(idx, aps_ctr1(step, dom, 0), key, &w0, &w1);
     return aps_u53(w0);
 }
+/* i.i.d. draws (multinomial, residual): draw i is word (i & 1) of block i >> 1 -- one Philox
+ * block serves two draws */
+static uint64_t draw_iid_u53(uint64_t key, uint64_t i, uint64_t step, uint32_t dom) {
+    uint64_t w[2];
+    aps_philox2x64(i >> 1, aps_ctr1(step, dom, 0), key, &w[0], &w[1]);
+    return aps_u53(w[i & 1]);
+}
 static uint64_t ceil_uq(uint64_t U, uint64_t Q) { /* ceil(U Q / 2^53) */
     u128 p = (u128)U * Q + (((u128)1 << 53) - 1);
     return (uint64_t)(p >> 53);
@@ -357,7 +364,7 @@ int orc_resample_multinomial_canon(const uint64_t *q, int64_t m, int64_t n, uint
     for (int64_t j = 0; j < m; ++j) { C += q[j]; cum[(size_t)j] = C; }
     if (C == 0) return 2;
     for (int64_t i = 0; i < n; ++i)
-        out[i] = canon_categorical(cum, draw_u53(key, (uint64_t)i, step, APS_DOM_RESAMPLE)) + 1;
+        out[i] = canon_categorical(cum, draw_iid_u53(key, (uint64_t)i, step, APS_DOM_RESAMPLE)) + 1;
     return 0;
 }
 
@@ -385,7 +392,7 @@ int orc_resample_residual_canon(const uint64_t *q, int64_t m, int64_t n, uint64_
         for (int64_t j = 0; j < m; ++j) { C += res[(size_t)j] >> sh; cum[(size_t)j] = C; }
         if (C == 0) return 2;
         for (int64_t r = 0; r < Rc; ++r, ++i)
-            out[i] = canon_categorical(cum, draw_u53(key, (uint64_t)r, step, APS_DOM_RESAMPLE)) + 1;
+            out[i] = canon_categorical(cum, draw_iid_u53(key, (uint64_t)r, step, APS_DOM_RESAMPLE)) + 1;
     }
     return 0;
 }
@@ -411,7 +418,8 @@ int orc_resample(int kind, int mode, const double *w, int64_t m, int64_t n, uint
         return orc_resample_systematic_seq(w, m, n, aps_u01(draw_u53(key, 0, step, APS_DOM_RESAMPLE) << 11), out);
     std::vector<double> us((size_t)(n > 0 ? n : 1));
     for (int64_t i = 0; i < n; ++i)
-        us[(size_t)i] = (double)(int64_t)draw_u53(key, (uint64_t)i, step, APS_DOM_RESAMPLE) * 0x1.0p-53;
+        us[(size_t)i] = (double)(int64_t)(kind == APS_RESAMPLE_STRATIFIED ? draw_u53(key, (uint64_t)i, step, APS_DOM_RESAMPLE)
+                                                                          : draw_iid_u53(key, (uint64_t)i, step, APS_DOM_RESAMPLE)) * 0x1.0p-53;
     switch (kind) {
         case APS_RESAMPLE_STRATIFIED: return orc_resample_stratified_seq(w, m, n, us.data(), out);
         case APS_RESAMPLE_MULTINOMIAL: return orc_resample_multinomial_seq(w, m, n, us.data(), out);
@@ -597,7 +605,9 @@ void resample_core(Sweep &sw, int64_t s) {
         } else {
             std::vector<double> us((size_t)(n > 0 ? n : 1));
             for (int64_t i = 0; i < n; ++i)
-                us[(size_t)i] = (double)(int64_t)draw_u53(sw.key, (uint64_t)i, (uint64_t)s, APS_DOM_RESAMPLE) * 0x1.0p-53;
+                us[(size_t)i] = (double)(int64_t)(kind == APS_RESAMPLE_STRATIFIED
+                                                      ? draw_u53(sw.key, (uint64_t)i, (uint64_t)s, APS_DOM_RESAMPLE)
+                                                      : draw_iid_u53(sw.key, (uint64_t)i, (uint64_t)s, APS_DOM_RESAMPLE)) * 0x1.0p-53;
             if (kind == APS_RESAMPLE_STRATIFIED) rc = orc_resample_stratified_seq(sw.w.data(), N, n, us.data(), indx.data());
             else if (kind == APS_RESAMPLE_MULTINOMIAL) rc = orc_resample_multinomial_seq(sw.w.data(), N, n, us.data(), indx.data());
             else rc = orc_resample_residual_seq(sw.w.data(), N, n, us.data(), indx.data());
