@@ -108,6 +108,10 @@ __global__ void __launch_bounds__(APS_K1_THREADS) k_propagate(const __grid_const
     const bool multi = c.world > 1;
     const u64 seq0 = multi ? c.sp->epoch * (u64)(c.T + 2) : 0ull;
     const long long xoff = xp - c.x;  // slab offset, identical on every rank
+    // the normals do not depend on the ancestors: draw the first pair's before waiting for the peers
+    long long p = (long long)blockIdx.x * APS_K1_THREADS + threadIdx.x;
+    double z[2 * D];
+    if (p < npairs) aps_pair_normals<D>(key, (u64)(pair0 + p), (u64)t, z);
     if (multi) {
         // the ancestor scatter of step t-1 (peer stores from every rank) must have landed: this
         // rank's resample kernel is complete (stream order), so block 0 tells every rank, and
@@ -121,10 +125,8 @@ __global__ void __launch_bounds__(APS_K1_THREADS) k_propagate(const __grid_const
             c.st->err = APS_ERR_COMM;
         __syncthreads();
     }
-    for (long long p = (long long)blockIdx.x * APS_K1_THREADS + threadIdx.x; p < npairs;
-         p += (long long)gridDim.x * APS_K1_THREADS) {
-        double z[2 * D];
-        aps_pair_normals<D>(key, (u64)(pair0 + p), (u64)t, z);
+    for (bool first = true; p < npairs; p += (long long)gridDim.x * APS_K1_THREADS, first = false) {
+        if (!first) aps_pair_normals<D>(key, (u64)(pair0 + p), (u64)t, z);
         const long long i0 = 2 * p;
         int2 a2 = make_int2(0, 0);
         if (t > 1) a2 = *reinterpret_cast<const int2 *>(anc + i0);
@@ -270,6 +272,14 @@ __global__ void __launch_bounds__(APS_K2_THREADS) k_normalise(const __grid_const
     unsigned bad_in = 0;
     const bool multi = c.world > 1;
     const u64 seq = multi ? c.sp->epoch * (u64)(c.T + 2) + (u64)s + 1 : 0ull;
+    double vin[APS_K2_IPT];  // this thread's inputs, loaded before the (sharded) wait for the maxima
+    if (INPUT != IN_Q) {
+#pragma unroll
+        for (int r = 0; r < APS_K2_IPT; ++r) {
+            const long long i = base + r * APS_K2_THREADS + threadIdx.x;
+            vin[r] = i < N ? in[i] : 0.0;
+        }
+    }
     if (multi) {
         // all-reduce(max): every block combines the shard maxima published by the propagate kernels
         __shared__ u64 s_m[APS_MAX_RANKS][4];
@@ -302,8 +312,8 @@ __global__ void __launch_bounds__(APS_K2_THREADS) k_normalise(const __grid_const
                 qi = c.q[i];
             } else {
                 double e;
-                if (INPUT == IN_LOGW) e = aps_exp(in[i] - M);
-                else e = in[i] / M;
+                if (INPUT == IN_LOGW) e = aps_exp(vin[r] - M);
+                else e = vin[r] / M;
                 qi = (e > 0.0) ? (u64)__double2ull_rz(e * scale) : 0ull;
                 c.q[i] = qi;
             }
@@ -606,7 +616,7 @@ __device__ __forceinline__ int children_below_fast(u64 C, u64 Q, int n, double r
 #define APS_TILE_BYTES (APS_TILE * 8)
 #define APS_K3_DYN_SMEM (APS_TILE_BYTES + APS_CAP * 4)
 template <int KIND, bool MULTI>
-__global__ void __launch_bounds__(APS_THREADS, 8) k_resample(const __grid_constant__ DevCtx c, const long long s,
+__global__ void __launch_bounds__(APS_THREADS, MULTI ? 6 : 8) k_resample(const __grid_constant__ DevCtx c, const long long s,
                                                              int32_t *__restrict__ anc_out,
                                                              const __grid_constant__ CUtensorMap tmap_q) {
     extern __shared__ __align__(1024) unsigned char dynsmem[];  // [tile: APS_TILE u64, swizzled][own: APS_CAP int]
@@ -619,48 +629,38 @@ __global__ void __launch_bounds__(APS_THREADS, 8) k_resample(const __grid_consta
     const StepPlan *pp = c.plan + s;
     const int tid = threadIdx.x;
     const long long base = (long long)blockIdx.x * APS_TILE;
-    u64 rank_off = 0;
-    if (MULTI) {
-        // sharded: combine the shard totals published by the normalise kernels of every rank
-        // (rank order; integers) and derive the plan locally -- identical on every rank
-        __shared__ StepPlan s_plan;
-        __shared__ u64 s_t[APS_MAX_RANKS][4];
-        __shared__ u64 s_off;
-        __shared__ int s_okt;
-        if (tid == 0) s_okt = 1;
-        __syncthreads();
-        if (blockIdx.x == 0) mail_post(c.peers, c.rank, c.world, 1, c.sp->epoch * (u64)(c.T + 2) + (u64)s + 1, c.acc[s].tot, 4);
-        if (!(c.dbg & 1) && !mail_wait(c.peers, c.rank, c.world, 1, c.sp->epoch * (u64)(c.T + 2) + (u64)s + 1, s_t, 4, c.st->spin)) s_okt = 0;
-        if (c.dbg & 1) { if (tid < c.world) { s_t[tid][0] = 1ull << 50; s_t[tid][1] = 1ull << 30; s_t[tid][2] = 1ull << 40; s_t[tid][3] = c.acc[s].max_enc; } }
-        __syncthreads();
-        if (tid == 0) {
-            u64 off;
-            multi_plan(c, s, s_t, s_okt != 0, &s_plan, &off);
-            s_off = off;
-            if (blockIdx.x == 0) {
-                c.acc[s].rank_off = off;
-                record_plan(c, s, s_plan);
-            }
-        }
-        __syncthreads();
-        pp = &s_plan;
-        rank_off = s_off;
-    }
-
     AncDst dst;
     dst.base = anc_out;
     dst.peers = (MULTI && !(c.dbg & 8)) ? c.peers : nullptr;
     dst.slab_off = anc_out - c.anc;
     dst.nl = (int)N;
     const int gbase = (int)(c.slot0 + base);  // global index of the tile's first parent
-    if (!pp->resampled || pp->err) {
-        // update_keys! branch (src/container.jl:247): every particle continues, weights kept
+    // update_keys! branch (src/container.jl:247): every particle continues, weights kept
+    auto identity_ancestors = [&]() {
 #pragma unroll
         for (int r = 0; r < APS_IPT; ++r) {
             const long long i = base + r * APS_THREADS + tid;
             if (i < N) anc_out[i] = (int32_t)(c.slot0 + i);
         }
-        return;
+    };
+    u64 Q, R, key;
+    int n, guard;
+    double ratio, roff;
+    auto load_plan = [&]() {
+        Q = pp->Q;
+        R = pp->R;
+        n = (int)pp->n;
+        guard = pp->guard;
+        ratio = pp->ratio;
+        roff = KIND == APS_RESAMPLE_SYSTEMATIC ? pp->roff : 0.0;
+        key = KIND == APS_RESAMPLE_STRATIFIED ? c.sp->key : 0ull;
+    };
+    if (!MULTI) {
+        if (!pp->resampled || pp->err) {
+            identity_ancestors();
+            return;
+        }
+        load_plan();
     }
     if (tid == 0) {
         if (smem_u32(tilebuf) & 1023u) __trap();  // the 128-byte swizzle pattern assumes a 1 KB aligned tile
@@ -674,13 +674,8 @@ __global__ void __launch_bounds__(APS_THREADS, 8) k_resample(const __grid_consta
         const long long pf = (long long)blockIdx.x + 2LL * 8 * 148;
         if (pf < (long long)gridDim.x) tma_prefetch_2d(&tmap_q, 0, (int)(pf * APS_THREADS));
     }
-    const u64 Q = pp->Q, R = pp->R;
-    const int n = (int)pp->n;
-    const int guard = pp->guard;
-    const double ratio = pp->ratio, roff = KIND == APS_RESAMPLE_SYSTEMATIC ? pp->roff : 0.0;
-    const u64 key = KIND == APS_RESAMPLE_STRATIFIED ? c.sp->key : 0ull;
     const u64 step = (u64)(s + c.ctr_offset);
-    const u64 tprefix = c.tile_prefix[blockIdx.x] + rank_off;
+    u64 tprefix = c.tile_prefix[blockIdx.x];
 
     zero_own(own);
     if (tid < 32) mbar_wait(&mbar, 0);  // one warp polls the mbarrier, the others park on the block barrier
@@ -700,7 +695,41 @@ __global__ void __launch_bounds__(APS_THREADS, 8) k_resample(const __grid_consta
 #pragma unroll
     for (int r = 1; r < APS_IPT; ++r) cum[r] += cum[r - 1];
     u64 tile_total;
-    const u64 excl = block_excl_scan_u64<APS_WARPS>(cum[APS_IPT - 1], red, &tile_total) + tprefix;  // syncs: own[] is zeroed
+    u64 excl = block_excl_scan_u64<APS_WARPS>(cum[APS_IPT - 1], red, &tile_total);  // syncs: own[] is zeroed
+
+    if (MULTI) {
+        // sharded: combine the shard totals published by the normalise kernels of every rank
+        // (rank order; integers) and derive the plan locally -- identical on every rank. The wait
+        // comes after the tile load and the local scan, which do not depend on the peers.
+        __shared__ StepPlan s_plan;
+        __shared__ u64 s_t[APS_MAX_RANKS][4];
+        __shared__ u64 s_off;
+        __shared__ int s_okt;
+        if (tid == 0) s_okt = 1;
+        __syncthreads();
+        if (blockIdx.x == 0) mail_post(c.peers, c.rank, c.world, 1, step_seq(c, s), c.acc[s].tot, 4);
+        if (!(c.dbg & 1) && !mail_wait(c.peers, c.rank, c.world, 1, step_seq(c, s), s_t, 4, c.st->spin)) s_okt = 0;
+        if (c.dbg & 1) { if (tid < c.world) { s_t[tid][0] = 1ull << 50; s_t[tid][1] = 1ull << 30; s_t[tid][2] = 1ull << 40; s_t[tid][3] = c.acc[s].max_enc; } }
+        __syncthreads();
+        if (tid == 0) {
+            u64 off;
+            multi_plan(c, s, s_t, s_okt != 0, &s_plan, &off);
+            s_off = off;
+            if (blockIdx.x == 0) {
+                c.acc[s].rank_off = off;
+                record_plan(c, s, s_plan);
+            }
+        }
+        __syncthreads();
+        pp = &s_plan;
+        tprefix += s_off;
+        if (!pp->resampled || pp->err) {
+            identity_ancestors();
+            return;
+        }
+        load_plan();
+    }
+    excl += tprefix;
 
     // ---- child range of the tile and of this thread (every thread evaluates the three bounds itself)
     const bool first_tile = blockIdx.x == 0 && c.slot0 == 0;  // K(C_{-1}) := 0 for the globally first parent

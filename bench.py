@@ -110,7 +110,7 @@ def make_data():
     return y
 
 
-def run_reference(args, rank):
+def run_reference(args, rank, emit=print):
     """--impl reference: the reference's CPU sweep. The reference itself (Julia) cannot run in this
     image, so this times the oracle port (oracle/aps_oracle.cpp), single thread -- the reference's
     sweep is serial (src/container.jl:194,264) -- on a bounded sample of the same workload."""
@@ -142,7 +142,7 @@ def run_reference(args, rank):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(out), flush=True)
+    emit(json.dumps(out))
 
 
 def cpu_baseline():
@@ -162,7 +162,21 @@ def cpu_baseline():
                       f"thread (the reference sweep is serial) of {os.cpu_count()} host cores"}
 
 
+def _quiet_stdout():
+    """Route fd 1 to stderr while the benchmark runs (NCCL and friends print banners to stdout)
+    and return a writer for the one JSON line on the real stdout."""
+    real = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(os.dup(2), "w")
+
+    def emit(line):
+        os.write(real, (line + "\n").encode())
+
+    return emit
+
+
 def main():
+    emit = _quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -177,7 +191,7 @@ def main():
     world = env_int("WORLD_SIZE", 1)
 
     if args.impl == "reference":
-        run_reference(args, rank)
+        run_reference(args, rank, emit)
         return
 
     import numpy as np
@@ -309,7 +323,7 @@ def main():
         }
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline()
-        print(json.dumps(out), flush=True)
+        emit(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
 
