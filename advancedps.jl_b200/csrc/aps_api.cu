@@ -134,6 +134,24 @@ static int enable_k3_smem() {
     return APS_OK;
 }
 
+// CUDA loads kernels lazily, and a first-time load may synchronise the context. Kernels that spin
+// on a peer (the sharded exchanges) must therefore never be launched for the first time while the
+// peer's matching kernel is still to be loaded by another thread of the same process: load the
+// kernels that run outside the captured sweep graph up front.
+static void preload_kernels() {
+    static bool done = false;
+    if (done) return;
+    cudaFuncAttributes a;
+    cudaFuncGetAttributes(&a, k_pick);
+    cudaFuncGetAttributes(&a, k_backtrace);
+    cudaFuncGetAttributes(&a, k_gather_final);
+    cudaFuncGetAttributes(&a, k_weights_out);
+    cudaFuncGetAttributes(&a, k_init_sweep);
+    cudaFuncGetAttributes(&a, k_plan_multi);
+    cudaGetLastError();
+    done = true;
+}
+
 static int g_sm_count = 0;
 static int sm_count() {
     if (g_sm_count == 0) {
@@ -323,6 +341,7 @@ extern "C" int aps_create(const aps_config *cfg, aps_handle **out) {
         free_handle(h);
         return APS_ERR_CUDA;
     }
+    preload_kernels();
     c.Y = h->d_Y;
     c.ref = h->d_ref;
     c.sp = h->d_sp;

@@ -57,10 +57,14 @@ __device__ __forceinline__ void st_sys_u64(u64 *p, u64 v) {
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
-// Exchanges are push + poll with no fences: a kernel's results are complete (and its peer stores
-// landed) when the NEXT kernel of the stream starts, so block 0 of the consumer kernel publishes
-// them to every rank's mailbox and all blocks of the consumer kernel, on every rank, spin on
-// their LOCAL mailbox until every rank's values for the expected sequence number are there.
+// Exchanges are push + poll with no system-scope fences. Scalars that a kernel reduces (the
+// log-weight maximum, the integer totals) are pushed to every rank's mailbox by the LAST block of
+// the producing kernel (device-scope ticket), so they travel over NVLink while the kernel drains
+// and the next one launches. The barrier after the ancestor scatter is different: the peer stores
+// of all blocks must have landed, which holds when the NEXT kernel of the stream starts, so block
+// 0 of the consumer kernel posts it. In both cases all blocks of the consumer kernel, on every
+// rank, spin on their LOCAL mailbox until every rank's values for the expected sequence number
+// are there.
 // Each value travels with its sequence number in one 16-byte store (one NVLink transaction), so
 // no ordering between separate stores is needed.
 __device__ __forceinline__ void st_pair_sys(ulonglong2 *p, u64 v, u64 seq) {
@@ -100,7 +104,8 @@ __device__ __forceinline__ bool mail_wait(const PeerTable *pt, int rank, int wor
             }
             out[r][k] = pr.x;
         }
-        if (spin && blockIdx.x == 0 && r == (rank + 1) % world) atomicAdd(&spin[kind], (unsigned long long)(clock64() - t0));
+        if (spin && kind < 4 && blockIdx.x == 0 && r == (rank + 1) % world)
+            atomicAdd(&spin[kind], (unsigned long long)(clock64() - t0));
     }
     return ok;
 }
@@ -112,7 +117,8 @@ struct StepAcc {
     unsigned int bad;  // NaN seen
     unsigned int done_ctr;      // last-block detection, normalise kernel
     unsigned int sel_done_ctr;  // last-block detection, categorical kernel
-    unsigned int pad0, pad1, pad2;
+    unsigned int k1_done;       // sharded: last-block detection of the propagate kernel (it posts the maximum)
+    unsigned int pad1, pad2;
     u64 tot[4];                 // sharded: this rank's integer totals (Q, Q1, Q2 | nan-flag) and the global max
     u64 rank_off;               // sharded: weight total of the lower ranks at this decision point
     long long child_off;        // sharded multinomial / residual: children owned by parents of lower ranks

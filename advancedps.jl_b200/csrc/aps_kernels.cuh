@@ -150,10 +150,15 @@ __global__ void __launch_bounds__(APS_K1_THREADS) k_propagate(const __grid_const
                 } else {
                     long long a = h ? a2.y : a2.x;  // global parent index
                     const double *xsrc = xp;
-                    if (multi && !(c.dbg & 4)) {  // the parent may live on a peer: read its state over NVLink
-                        const int owner = (int)((unsigned)a / (unsigned)N);
-                        a -= (long long)owner * N;
-                        xsrc = c.peers->x[owner] + xoff;
+                    if (multi && !(c.dbg & 4)) {
+                        const unsigned al = (unsigned)(a - c.slot0);
+                        if (al < (unsigned)N) {
+                            a = al;  // own shard (the common case)
+                        } else {     // the parent lives on a peer: read its state over NVLink
+                            const int owner = (int)((unsigned)a / (unsigned)N);
+                            a -= (long long)owner * N;
+                            xsrc = c.peers->x[owner] + xoff;
+                        }
                     }
                     double xpv[D];
 #pragma unroll
@@ -182,6 +187,23 @@ __global__ void __launch_bounds__(APS_K1_THREADS) k_propagate(const __grid_const
     if (threadIdx.x == 0) {
         if (bmax) atomicMax(&c.acc[t].max_enc, bmax);
         if (bad) atomicOr(&c.acc[t].bad, 1u);
+    }
+    if (multi) {
+        // all-reduce(max), producer side: the last block to finish publishes this shard's maximum
+        // to every rank, so it is on its way while this kernel drains and k_normalise launches
+        __shared__ unsigned s_lastb;
+        __shared__ u64 s_pub[2];
+        if (threadIdx.x == 0) {
+            __threadfence();
+            s_lastb = atomicAdd(&c.acc[t].k1_done, 1u) == gridDim.x - 1 ? 1u : 0u;
+            if (s_lastb) {
+                __threadfence();
+                s_pub[0] = atomicMax(&c.acc[t].max_enc, 0ull);
+                s_pub[1] = (u64)atomicOr(&c.acc[t].bad, 0u);
+            }
+        }
+        __syncthreads();
+        if (s_lastb) mail_post(c.peers, c.rank, c.world, 0, seq0 + (u64)t + 1, s_pub, 2);
     }
     probe.end();
 }
@@ -286,10 +308,7 @@ __global__ void __launch_bounds__(APS_K2_THREADS) k_normalise(const __grid_const
         __shared__ int s_okm;
         if (threadIdx.x == 0) s_okm = 1;
         __syncthreads();
-        if (blockIdx.x == 0) {  // the propagate kernel of this rank is complete: publish its maximum
-            const u64 v[2] = {max_enc, (u64)acc->bad};
-            mail_post(c.peers, c.rank, c.world, 0, seq, v, 2);
-        }
+        // (published by the last block of every rank's propagate kernel)
         if (!(c.dbg & 1) && !mail_wait(c.peers, c.rank, c.world, 0, seq, s_m, 2, c.st ? c.st->spin : nullptr)) s_okm = 0;
         if (c.dbg & 1) { if (threadIdx.x < c.world) { s_m[threadIdx.x][0] = acc->max_enc; s_m[threadIdx.x][1] = 0; } }
         __syncthreads();
@@ -360,12 +379,15 @@ __global__ void __launch_bounds__(APS_K2_THREADS) k_normalise(const __grid_const
     if (multi) {
         // this rank's totals, published by block 0 of the resample kernel (Q2 < 2^63: its top bit
         // carries the NaN flag; tot[3] = the already global maximum)
+        __shared__ u64 s_tot[4];
         if (threadIdx.x == 0) {
-            acc->tot[0] = Q;
-            acc->tot[1] = Q1;
-            acc->tot[2] = Q2 | ((u64)((acc->bad | bad_in) ? 1 : 0) << 63);
-            acc->tot[3] = max_enc;
+            s_tot[0] = acc->tot[0] = Q;
+            s_tot[1] = acc->tot[1] = Q1;
+            s_tot[2] = acc->tot[2] = Q2 | ((u64)((acc->bad | bad_in) ? 1 : 0) << 63);
+            s_tot[3] = acc->tot[3] = max_enc;
         }
+        __syncthreads();
+        mail_post(c.peers, c.rank, c.world, 1, seq, s_tot, 4);  // all-gather of the totals, producer side
         return;
     }
     if (threadIdx.x == 0) {
@@ -413,9 +435,9 @@ __device__ __forceinline__ void multi_plan(const DevCtx &c, long long s, const u
 // this rank's weight offset in global memory for the kernels that follow
 __global__ void __launch_bounds__(32) k_plan_multi(const __grid_constant__ DevCtx c, const long long s) {
     __shared__ u64 s_t[APS_MAX_RANKS][4];
-    __shared__ u64 s_v[4];
-    if (threadIdx.x < 4) s_v[threadIdx.x] = c.acc[s].tot[threadIdx.x];
-    const bool ok = block_exchange(c, 1, step_seq(c, s), s_v, 4, s_t);
+    bool ok = true;  // the totals were published by the last block of every rank's normalise kernel
+    if (!(c.dbg & 1)) ok = mail_wait(c.peers, c.rank, c.world, 1, step_seq(c, s), s_t, 4, c.st->spin);
+    ok = __syncthreads_and(ok ? 1 : 0) != 0;
     if (threadIdx.x == 0) {
         StepPlan p;
         u64 off;
@@ -488,8 +510,11 @@ struct AncDst {
     const PeerTable *peers;   // null on one GPU
     long long slab_off;       // offset of the slab inside each rank's ancestor store
     int nl;                   // slots per rank
+    int lo;                   // first global slot of this rank
     __device__ __forceinline__ int32_t *at(int g) const {
         if (!peers) return base + g;
+        const unsigned gl = (unsigned)(g - lo);
+        if (gl < (unsigned)nl) return base + gl;  // own shard (the common case)
         const int owner = (int)((unsigned)g / (unsigned)nl);
         return peers->anc[owner] + slab_off + (g - owner * nl);
     }
@@ -634,6 +659,7 @@ __global__ void __launch_bounds__(APS_THREADS, MULTI ? 6 : 8) k_resample(const _
     dst.peers = (MULTI && !(c.dbg & 8)) ? c.peers : nullptr;
     dst.slab_off = anc_out - c.anc;
     dst.nl = (int)N;
+    dst.lo = (int)c.slot0;
     const int gbase = (int)(c.slot0 + base);  // global index of the tile's first parent
     // update_keys! branch (src/container.jl:247): every particle continues, weights kept
     auto identity_ancestors = [&]() {
@@ -707,7 +733,6 @@ __global__ void __launch_bounds__(APS_THREADS, MULTI ? 6 : 8) k_resample(const _
         __shared__ int s_okt;
         if (tid == 0) s_okt = 1;
         __syncthreads();
-        if (blockIdx.x == 0) mail_post(c.peers, c.rank, c.world, 1, step_seq(c, s), c.acc[s].tot, 4);
         if (!(c.dbg & 1) && !mail_wait(c.peers, c.rank, c.world, 1, step_seq(c, s), s_t, 4, c.st->spin)) s_okt = 0;
         if (c.dbg & 1) { if (tid < c.world) { s_t[tid][0] = 1ull << 50; s_t[tid][1] = 1ull << 30; s_t[tid][2] = 1ull << 40; s_t[tid][3] = c.acc[s].max_enc; } }
         __syncthreads();
@@ -949,6 +974,7 @@ __global__ void __launch_bounds__(APS_THREADS) k_expand_counts(const __grid_cons
     dst.peers = (multi && !(c.dbg & 8)) ? c.peers : nullptr;
     dst.slab_off = multi ? anc_out - c.anc : 0;
     dst.nl = (int)a.N;
+    dst.lo = (int)slot0;
     expand_tile_general(khi, excl, kA, kB, (int)(slot0 + base), dst, own, wmax);
     const long long n = a.plan->n;
     if (identity_if_not_resampled && blockIdx.x == gridDim.x - 1 && tid == 0) {  // reference particle: globally last slot
@@ -1104,10 +1130,15 @@ __device__ __forceinline__ double pgas_logweight(const DevCtx &c, long long s, l
     const long long N = c.NS;
     long long a = anc_cur[i];  // global index of the parent in set s-1
     const double *xsrc = xpp;
-    if (c.world > 1) {  // the parent may live on a peer: read its state over NVLink
-        const int owner = (int)((unsigned)a / (unsigned)c.N);
-        a -= (long long)owner * c.N;
-        xsrc = c.peers->x[owner] + (xpp - c.x);
+    if (c.world > 1) {
+        const unsigned al = (unsigned)(a - c.slot0);
+        if (al < (unsigned)c.N) {
+            a = al;  // own shard
+        } else {     // the parent lives on a peer: read its state over NVLink
+            const int owner = (int)((unsigned)a / (unsigned)c.N);
+            a -= (long long)owner * c.N;
+            xsrc = c.peers->x[owner] + (xpp - c.x);
+        }
     }
     double xp[D], xr[D];
 #pragma unroll
