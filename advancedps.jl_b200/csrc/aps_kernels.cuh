@@ -88,7 +88,7 @@ __global__ void k_init_sweep(const __grid_constant__ DevCtx c) {
 // Box-Muller normals (aps_pair_normals), ancestors / log-weights / states move as 8- and 16-byte
 // vectors. Block maxima of the new log-weights are folded into one atomicMax per block.
 template <int D, int DY, int OBS>
-__global__ void __launch_bounds__(APS_K1_THREADS) k_propagate(const __grid_constant__ DevCtx c, const long long t,
+__global__ void __launch_bounds__(APS_K1_THREADS, D >= 3 ? 3 : 1) k_propagate(const __grid_constant__ DevCtx c, const long long t,
                                                            double *__restrict__ xt, const double *__restrict__ xp,
                                                            const int32_t *__restrict__ anc) {
     __shared__ u64 red[APS_K1_THREADS / 32];
