@@ -99,10 +99,10 @@ static int make_q_tensormap(CUtensorMap *out, u64 *q, long long n_padded) {
             return fail(APS_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
         enc = (encode_tiled_fn)fn;
     }
-    const cuuint64_t rows = (cuuint64_t)((n_padded + APS_IPT - 1) / APS_IPT);
-    const cuuint64_t gdim[2] = {APS_IPT, rows};
-    const cuuint64_t gstride[1] = {APS_IPT * 8};
-    const cuuint32_t box[2] = {APS_IPT, APS_THREADS};
+    const cuuint64_t rows = (cuuint64_t)((n_padded + APS_ROW - 1) / APS_ROW);
+    const cuuint64_t gdim[2] = {APS_ROW, rows};
+    const cuuint64_t gstride[1] = {APS_ROW * 8};
+    const cuuint32_t box[2] = {APS_ROW, APS_TILE / APS_ROW};
     const cuuint32_t estride[2] = {1, 1};
     CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_UINT64, 2, q, gdim, gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -425,7 +425,7 @@ static long long enqueue_sweep(aps_handle *h, LaunchProf *prof = nullptr) {
         APS_LAUNCH(0, h->f_prop<<<gk1, APS_K1_THREADS, 0, st>>>(c, t, x_slab(t), x_slab(t - 1), anc_slab(t - 1)));
         APS_LAUNCH(1, k_normalise<IN_LOGW><<<gt, APS_K2_THREADS, 0, st>>>(c, c.logw, t));
         if (c.resampler == APS_RESAMPLE_SYSTEMATIC || c.resampler == APS_RESAMPLE_STRATIFIED) {
-            APS_LAUNCH(2, h->f_res<<<gt, APS_THREADS, APS_K3_DYN_SMEM, st>>>(c, t, anc_slab(t), h->tmap_q));
+            APS_LAUNCH(2, h->f_res<<<gt, APS_K3_THREADS, APS_K3_DYN_SMEM, st>>>(c, t, anc_slab(t), h->tmap_q));
         } else {
             const bool multi = c.world > 1;
             MultiArgs a;
@@ -864,7 +864,7 @@ extern "C" int aps_resample(int kind, const double *wts, int64_t m, int64_t n, u
         if (rc) return rc;
         rc = enable_k3_smem();
         if (rc) return rc;
-        pick_resample(kind)<<<(int)c.num_tiles, APS_THREADS, APS_K3_DYN_SMEM, w.stream>>>(c, 0, w.d_idx32, w.tmap_q);
+        pick_resample(kind)<<<(int)c.num_tiles, APS_K3_THREADS, APS_K3_DYN_SMEM, w.stream>>>(c, 0, w.d_idx32, w.tmap_q);
     } else {
         const int gt = (int)c.num_tiles;
         MultiArgs a;
@@ -1047,7 +1047,7 @@ extern "C" int aps_bench_resample(int kind, int64_t n, int iters, int flush_l2, 
     for (int it = -3; it < iters; ++it) {  // 3 warm-up launches
         if (flush_l2) CU(cudaMemsetAsync(flush, it & 0xff, flush_bytes, w.stream));
         CU(cudaEventRecord(e0, w.stream));
-        f<<<(int)c.num_tiles, APS_THREADS, APS_K3_DYN_SMEM, w.stream>>>(c, 0, w.d_idx32, w.tmap_q);
+        f<<<(int)c.num_tiles, APS_K3_THREADS, APS_K3_DYN_SMEM, w.stream>>>(c, 0, w.d_idx32, w.tmap_q);
         CU(cudaEventRecord(e1, w.stream));
         CU(cudaStreamSynchronize(w.stream));
         float ms = 0.f;

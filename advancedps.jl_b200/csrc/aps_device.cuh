@@ -21,6 +21,22 @@ typedef unsigned long long u64;
 #define APS_CPT 20              // child slots per thread in one expand pass
 #define APS_CAP (APS_THREADS * APS_CPT)    // 2560 children staged per pass
 #define APS_WARPS (APS_THREADS / 32)
+#define APS_ROW 16              // u64 per 128-byte row of the TMA box; a tile is APS_TILE / APS_ROW = 128 rows
+// geometry of the systematic / stratified resample kernel. Measured at N = 2^25 (L2 flushed):
+// 128 threads x 16 parents, 8 blocks/SM: 95.9 us; 256 x 8 at 4 / 5 / 6 blocks/SM: 105 / 110 / 119 us
+// (more warps in flight, but twice the block-scan and expand-scan overhead per parent).
+#ifndef APS_K3_THREADS
+#define APS_K3_THREADS 128
+#endif
+#define APS_K3_IPT (APS_TILE / APS_K3_THREADS)      // parents per thread
+#ifndef APS_K3_CPT
+#define APS_K3_CPT 20                               // child slots per thread in one expand pass
+#endif
+#define APS_K3_CAP (APS_K3_THREADS * APS_K3_CPT)    // children staged per pass
+#define APS_K3_WARPS (APS_K3_THREADS / 32)
+#ifndef APS_K3_MINBLOCKS
+#define APS_K3_MINBLOCKS 8
+#endif
 #define APS_K1_THREADS 256      // threads per block of the grid-stride kernels (propagate, maxima)
 
 // ---------------------------------------------------------------- multi-GPU sharding (one process per GPU)

@@ -88,7 +88,7 @@ __global__ void k_init_sweep(const __grid_constant__ DevCtx c) {
 // Box-Muller normals (aps_pair_normals), ancestors / log-weights / states move as 8- and 16-byte
 // vectors. Block maxima of the new log-weights are folded into one atomicMax per block.
 template <int D, int DY, int OBS>
-__global__ void __launch_bounds__(APS_K1_THREADS, D >= 3 ? 3 : 1) k_propagate(const __grid_constant__ DevCtx c, const long long t,
+__global__ void __launch_bounds__(APS_K1_THREADS) k_propagate(const __grid_constant__ DevCtx c, const long long t,
                                                            double *__restrict__ xt, const double *__restrict__ xp,
                                                            const int32_t *__restrict__ anc) {
     __shared__ u64 red[APS_K1_THREADS / 32];
@@ -521,17 +521,19 @@ struct AncDst {
 };
 
 // scan + store for the child slots [cb, cb + cnt) whose markers are already in own[]
+template <int TH, int CPT>
 __device__ __forceinline__ void expand_scan_store(int cb, int cnt, int kA, int kB, int base, const AncDst &dst, int *own,
                                                   int *wmax) {
+    constexpr int WARPS = TH / 32;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int4 *own4 = reinterpret_cast<const int4 *>(own);
-    const bool active = tid * APS_CPT < cnt;
-    int v[APS_CPT];
+    const bool active = tid * CPT < cnt;
+    int v[CPT];
     int run = 0;
     if (active) {
 #pragma unroll
-        for (int m = 0; m < APS_CPT / 4; ++m) {
-            const int4 t = own4[tid * (APS_CPT / 4) + m];
+        for (int m = 0; m < CPT / 4; ++m) {
+            const int4 t = own4[tid * (CPT / 4) + m];
             run = max(run, t.x); v[4 * m] = run;
             run = max(run, t.y); v[4 * m + 1] = run;
             run = max(run, t.z); v[4 * m + 2] = run;
@@ -549,20 +551,20 @@ __device__ __forceinline__ void expand_scan_store(int cb, int cnt, int kA, int k
     if (lane == 0) excl = 0;
     __syncthreads();
     {
-        int w = wmax[lane & (APS_WARPS - 1)];
+        int w = wmax[lane & (WARPS - 1)];
 #pragma unroll
-        for (int o = 1; o < APS_WARPS; o <<= 1) {
-            const int tt = __shfl_up_sync(0xffffffffu, w, o, APS_WARPS);
-            if ((lane & (APS_WARPS - 1)) >= o) w = max(w, tt);
+        for (int o = 1; o < WARPS; o <<= 1) {
+            const int tt = __shfl_up_sync(0xffffffffu, w, o, WARPS);
+            if ((lane & (WARPS - 1)) >= o) w = max(w, tt);
         }
-        const int prev = __shfl_sync(0xffffffffu, w, (warp + APS_WARPS - 1) & (APS_WARPS - 1), APS_WARPS);
+        const int prev = __shfl_sync(0xffffffffu, w, (warp + WARPS - 1) & (WARPS - 1), WARPS);
         if (warp > 0) excl = max(excl, prev);
     }
     if (active) {
         const int add = base - 1;
 #pragma unroll
-        for (int m = 0; m < APS_CPT / 4; ++m) {
-            const int g = cb + tid * APS_CPT + 4 * m;  // global child index of this vector, multiple of 4
+        for (int m = 0; m < CPT / 4; ++m) {
+            const int g = cb + tid * CPT + 4 * m;  // global child index of this vector, multiple of 4
             int4 o;
             o.x = max(v[4 * m], excl) + add;
             o.y = max(v[4 * m + 1], excl) + add;
@@ -581,32 +583,35 @@ __device__ __forceinline__ void expand_scan_store(int cb, int cnt, int kA, int k
     }
 }
 
+template <int CPT>
 __device__ __forceinline__ void zero_own(int *own) {
     int4 *own4 = reinterpret_cast<int4 *>(own);
     const int4 z = make_int4(0, 0, 0, 0);
 #pragma unroll
-    for (int m = 0; m < APS_CPT / 4; ++m) own4[threadIdx.x * (APS_CPT / 4) + m] = z;
+    for (int m = 0; m < CPT / 4; ++m) own4[threadIdx.x * (CPT / 4) + m] = z;
 }
 
 // general (rare) path: any number of children, clipped chunk by chunk. khi: inclusive child
 // counts of this thread's parents, klo0: count below its first parent.
+template <int TH, int IPT, int CPT>
 __device__ __noinline__ void expand_tile_general(const int *khi, int klo0, int kA, int kB, int base, const AncDst &dst,
                                                  int *own, int *wmax) {
+    constexpr int CAP = TH * CPT;
     const int tid = threadIdx.x;
-    for (int cb = kA & ~3; cb < kB; cb += APS_CAP) {
-        const int cnt = (kB - cb) < APS_CAP ? (kB - cb) : APS_CAP;
+    for (int cb = kA & ~3; cb < kB; cb += CAP) {
+        const int cnt = (kB - cb) < CAP ? (kB - cb) : CAP;
         __syncthreads();
-        zero_own(own);
+        zero_own<CPT>(own);
         __syncthreads();
         int klo = klo0;
-        for (int j = 0; j < APS_IPT; ++j) {
+        for (int j = 0; j < IPT; ++j) {
             const int kh = khi[j];
             const int lo_rel = klo - cb, hi_rel = kh - cb;
-            if (kh > klo && hi_rel > 0 && lo_rel < cnt) own[lo_rel > 0 ? lo_rel : 0] = tid * APS_IPT + j + 1;
+            if (kh > klo && hi_rel > 0 && lo_rel < cnt) own[lo_rel > 0 ? lo_rel : 0] = tid * IPT + j + 1;
             klo = kh;
         }
         __syncthreads();
-        expand_scan_store(cb, cnt, kA, kB, base, dst, own, wmax);
+        expand_scan_store<TH, CPT>(cb, cnt, kA, kB, base, dst, own, wmax);
     }
 }
 
@@ -639,14 +644,14 @@ __device__ __forceinline__ int children_below_fast(u64 C, u64 Q, int n, double r
 // i.e. 16 consecutive weights -- free of bank conflicts. Rows past the end of the tensor are
 // zero-filled by the hardware, so ragged tails need no special case.
 #define APS_TILE_BYTES (APS_TILE * 8)
-#define APS_K3_DYN_SMEM (APS_TILE_BYTES + APS_CAP * 4)
+#define APS_K3_DYN_SMEM (APS_TILE_BYTES + APS_K3_CAP * 4)
 template <int KIND, bool MULTI>
-__global__ void __launch_bounds__(APS_THREADS, MULTI ? 6 : 8) k_resample(const __grid_constant__ DevCtx c, const long long s,
+__global__ void __launch_bounds__(APS_K3_THREADS, MULTI ? APS_K3_MINBLOCKS - 2 : APS_K3_MINBLOCKS) k_resample(const __grid_constant__ DevCtx c, const long long s,
                                                              int32_t *__restrict__ anc_out,
                                                              const __grid_constant__ CUtensorMap tmap_q) {
-    extern __shared__ __align__(1024) unsigned char dynsmem[];  // [tile: APS_TILE u64, swizzled][own: APS_CAP int]
-    __shared__ u64 red[APS_THREADS / 32];
-    __shared__ int wmax[APS_THREADS / 32];
+    extern __shared__ __align__(1024) unsigned char dynsmem[];  // [tile: APS_TILE u64, swizzled][own: APS_K3_CAP int]
+    __shared__ u64 red[APS_K3_WARPS];
+    __shared__ int wmax[APS_K3_WARPS];
     __shared__ __align__(8) uint64_t mbar;
     unsigned char *tilebuf = dynsmem;
     int *own = reinterpret_cast<int *>(dynsmem + APS_TILE_BYTES);
@@ -664,8 +669,8 @@ __global__ void __launch_bounds__(APS_THREADS, MULTI ? 6 : 8) k_resample(const _
     // update_keys! branch (src/container.jl:247): every particle continues, weights kept
     auto identity_ancestors = [&]() {
 #pragma unroll
-        for (int r = 0; r < APS_IPT; ++r) {
-            const long long i = base + r * APS_THREADS + tid;
+        for (int r = 0; r < APS_K3_IPT; ++r) {
+            const long long i = base + r * APS_K3_THREADS + tid;
             if (i < N) anc_out[i] = (int32_t)(c.slot0 + i);
         }
     };
@@ -695,33 +700,36 @@ __global__ void __launch_bounds__(APS_THREADS, MULTI ? 6 : 8) k_resample(const _
     __syncthreads();
     if (tid == 0) {
         mbar_expect_tx(&mbar, APS_TILE_BYTES);
-        tma_load_2d(tilebuf, &tmap_q, &mbar, 0, (int)(base / APS_IPT));
+        tma_load_2d(tilebuf, &tmap_q, &mbar, 0, (int)(base / APS_ROW));
         // pull the tile that a block ~2 residency waves later will need from HBM into L2 now
-        const long long pf = (long long)blockIdx.x + 2LL * 8 * 148;
-        if (pf < (long long)gridDim.x) tma_prefetch_2d(&tmap_q, 0, (int)(pf * APS_THREADS));
+        const long long pf = (long long)blockIdx.x + 2LL * APS_K3_MINBLOCKS * 148;
+        if (pf < (long long)gridDim.x) tma_prefetch_2d(&tmap_q, 0, (int)(pf * (APS_TILE / APS_ROW)));
     }
     const u64 step = (u64)(s + c.ctr_offset);
     u64 tprefix = c.tile_prefix[blockIdx.x];
 
-    zero_own(own);
+    zero_own<APS_K3_CPT>(own);
     if (tid < 32) mbar_wait(&mbar, 0);  // one warp polls the mbarrier, the others park on the block barrier
     __syncthreads();
 
-    // ---- this thread's 16 consecutive integer weights (row tid of the swizzled tile), local inclusive sums
-    u64 cum[APS_IPT];
+    // ---- this thread's APS_K3_IPT consecutive integer weights (its part of one 128-byte row of the
+    //      swizzled tile: 16-byte chunk c of row r sits at chunk position c ^ (r & 7)), local inclusive sums
+    u64 cum[APS_K3_IPT];
     {
-        const unsigned char *row = tilebuf + tid * (APS_IPT * 8);
+        const int rowi = (tid * APS_K3_IPT) / APS_ROW;
+        const int chunk0 = ((tid * APS_K3_IPT) % APS_ROW) / 2;
+        const unsigned char *row = tilebuf + rowi * (APS_ROW * 8);
 #pragma unroll
-        for (int r = 0; r < APS_IPT / 2; ++r) {
-            const ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(row + ((r ^ (tid & 7)) << 4));
+        for (int r = 0; r < APS_K3_IPT / 2; ++r) {
+            const ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(row + (((chunk0 + r) ^ (rowi & 7)) << 4));
             cum[2 * r] = v.x;
             cum[2 * r + 1] = v.y;
         }
     }
 #pragma unroll
-    for (int r = 1; r < APS_IPT; ++r) cum[r] += cum[r - 1];
+    for (int r = 1; r < APS_K3_IPT; ++r) cum[r] += cum[r - 1];
     u64 tile_total;
-    u64 excl = block_excl_scan_u64<APS_WARPS>(cum[APS_IPT - 1], red, &tile_total);  // syncs: own[] is zeroed
+    u64 excl = block_excl_scan_u64<APS_K3_WARPS>(cum[APS_K3_IPT - 1], red, &tile_total);  // syncs: own[] is zeroed
 
     if (MULTI) {
         // sharded: combine the shard totals published by the normalise kernels of every rank
@@ -763,20 +771,20 @@ __global__ void __launch_bounds__(APS_THREADS, MULTI ? 6 : 8) k_resample(const _
     const int kB = children_below_fast<KIND>(tprefix + tile_total, Q, n, ratio, roff, guard, key, step, &unsafe);
     int klo = tid == 0 ? kA : children_below_fast<KIND>(excl, Q, n, ratio, roff, guard, key, step, &unsafe);
     const int cb = kA & ~3;
-    const bool single = kB - cb <= APS_CAP;
+    const bool single = kB - cb <= APS_K3_CAP;
 
     // ---- fast path: estimate the children below each parent and drop its marker at once
     if (single) {
 #pragma unroll
-        for (int r = 0; r < APS_IPT; ++r) {
+        for (int r = 0; r < APS_K3_IPT; ++r) {
             const int k = children_below_fast<KIND>(excl + cum[r], Q, n, ratio, roff, guard, key, step, &unsafe);
-            if (k > klo) own[klo - cb] = tid * APS_IPT + r + 1;
+            if (k > klo) own[klo - cb] = tid * APS_K3_IPT + r + 1;
             klo = k;
         }
     }
     const int slow = __syncthreads_or((unsafe || !single) ? 1 : 0);
     if (!slow) {
-        expand_scan_store(cb, kB - cb, kA, kB, gbase, dst, own, wmax);
+        expand_scan_store<APS_K3_THREADS, APS_K3_CPT>(cb, kB - cb, kA, kB, gbase, dst, own, wmax);
     } else {
         // ---- retry (some estimate fell within the guard band of an integer, or the tile owns
         //      more children than one pass holds): same walk with exact fix-ups where needed
@@ -784,21 +792,21 @@ __global__ void __launch_bounds__(APS_THREADS, MULTI ? 6 : 8) k_resample(const _
         const int kBx = children_below_checked<KIND>(tprefix + tile_total, Q, R, n, ratio, roff, guard, key, step);
         int klx = tid == 0 ? kAx : children_below_checked<KIND>(excl, Q, R, n, ratio, roff, guard, key, step);
         const int cbx = kAx & ~3;
-        if (kBx - cbx <= APS_CAP) {
-            zero_own(own);  // every thread is past the marker loop (the __syncthreads_or above)
+        if (kBx - cbx <= APS_K3_CAP) {
+            zero_own<APS_K3_CPT>(own);  // every thread is past the marker loop (the __syncthreads_or above)
             __syncthreads();
-            for (int r = 0; r < APS_IPT; ++r) {
+            for (int r = 0; r < APS_K3_IPT; ++r) {
                 const int k = children_below_checked<KIND>(excl + cum[r], Q, R, n, ratio, roff, guard, key, step);
-                if (k > klx) own[klx - cbx] = tid * APS_IPT + r + 1;
+                if (k > klx) own[klx - cbx] = tid * APS_K3_IPT + r + 1;
                 klx = k;
             }
             __syncthreads();
-            expand_scan_store(cbx, kBx - cbx, kAx, kBx, gbase, dst, own, wmax);
+            expand_scan_store<APS_K3_THREADS, APS_K3_CPT>(cbx, kBx - cbx, kAx, kBx, gbase, dst, own, wmax);
         } else {
-            int khi[APS_IPT];
-            for (int r = 0; r < APS_IPT; ++r)
+            int khi[APS_K3_IPT];
+            for (int r = 0; r < APS_K3_IPT; ++r)
                 khi[r] = children_below_checked<KIND>(excl + cum[r], Q, R, n, ratio, roff, guard, key, step);
-            expand_tile_general(khi, klx, kAx, kBx, gbase, dst, own, wmax);
+            expand_tile_general<APS_K3_THREADS, APS_K3_IPT, APS_K3_CPT>(khi, klx, kAx, kBx, gbase, dst, own, wmax);
         }
     }
 
@@ -975,7 +983,7 @@ __global__ void __launch_bounds__(APS_THREADS) k_expand_counts(const __grid_cons
     dst.slab_off = multi ? anc_out - c.anc : 0;
     dst.nl = (int)a.N;
     dst.lo = (int)slot0;
-    expand_tile_general(khi, excl, kA, kB, (int)(slot0 + base), dst, own, wmax);
+    expand_tile_general<APS_THREADS, APS_IPT, APS_CPT>(khi, excl, kA, kB, (int)(slot0 + base), dst, own, wmax);
     const long long n = a.plan->n;
     if (identity_if_not_resampled && blockIdx.x == gridDim.x - 1 && tid == 0) {  // reference particle: globally last slot
         if (!multi && n < a.N) anc_out[a.N - 1] = (int32_t)(a.N - 1);
