@@ -241,8 +241,10 @@ def randcat(w, key=0, ctr=0):
     return out.value
 
 
-def bench_resample(kind, n, iters=20, flush_l2=True, seed=1):
+def bench_resample(kind, n, iters=20, flush_l2=2, seed=1):
+    """flush_l2: 0 none, 1 write 512 MB between launches (L2 left full of dirty lines),
+    2 write 512 MB then stream-read 256 MB (L2 cold and clean)."""
     avg, mn = C.c_float(), C.c_float()
-    check(lib().aps_bench_resample(int(kind), C.c_int64(n), int(iters), int(bool(flush_l2)), C.c_uint64(seed),
+    check(lib().aps_bench_resample(int(kind), C.c_int64(n), int(iters), int(flush_l2), C.c_uint64(seed),
                                    C.byref(avg), C.byref(mn)))
     return avg.value, mn.value

@@ -34,6 +34,9 @@ typedef unsigned long long u64;
 #endif
 #define APS_K3_CAP (APS_K3_THREADS * APS_K3_CPT)    // children staged per pass
 #define APS_K3_WARPS (APS_K3_THREADS / 32)
+#ifndef APS_K3_PF_WAVES
+#define APS_K3_PF_WAVES 0       // L2 prefetch distance of the tile loads, in residency waves (measured at N = 2^25: 0: 84.2 us, 1: 86.1, 2: 93.2, 4: 99.9)
+#endif
 #ifndef APS_K3_MINBLOCKS
 #define APS_K3_MINBLOCKS 8
 #endif

@@ -520,17 +520,39 @@ struct AncDst {
     }
 };
 
+// Marker array layout. Parents are thread-blocked (16 consecutive parents per thread), so in one
+// marker round the lanes of a warp write child positions about 16 apart: with a plain layout they
+// fall into two banks (16-way conflicts; ncu: 1/3 of all shared-memory wavefronts of the kernel).
+// One pad word per 32 positions spreads a stride-16 pattern over all 32 banks.
+#ifndef APS_OWN_PAD
+#define APS_OWN_PAD 0   // measured: 98.2 us padded (scalar read-back) vs 95.9 us plain at N = 2^25
+#endif
+#if APS_OWN_PAD
+#define APS_OWN_WORDS(cap) ((((cap) + ((cap) >> 5) + 1) + 3) & ~3)
+__device__ __forceinline__ int own_idx(int p) { return p + (p >> 5); }
+#else
+#define APS_OWN_WORDS(cap) (cap)
+__device__ __forceinline__ int own_idx(int p) { return p; }
+#endif
+
 // scan + store for the child slots [cb, cb + cnt) whose markers are already in own[]
 template <int TH, int CPT>
 __device__ __forceinline__ void expand_scan_store(int cb, int cnt, int kA, int kB, int base, const AncDst &dst, int *own,
                                                   int *wmax) {
     constexpr int WARPS = TH / 32;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int4 *own4 = reinterpret_cast<const int4 *>(own);
     const bool active = tid * CPT < cnt;
     int v[CPT];
     int run = 0;
     if (active) {
+#if APS_OWN_PAD
+#pragma unroll
+        for (int j = 0; j < CPT; ++j) {
+            run = max(run, own[own_idx(tid * CPT + j)]);
+            v[j] = run;
+        }
+#else
+        const int4 *own4 = reinterpret_cast<const int4 *>(own);
 #pragma unroll
         for (int m = 0; m < CPT / 4; ++m) {
             const int4 t = own4[tid * (CPT / 4) + m];
@@ -539,6 +561,7 @@ __device__ __forceinline__ void expand_scan_store(int cb, int cnt, int kA, int k
             run = max(run, t.z); v[4 * m + 2] = run;
             run = max(run, t.w); v[4 * m + 3] = run;
         }
+#endif
     }
     int inc = run;
 #pragma unroll
@@ -583,12 +606,19 @@ __device__ __forceinline__ void expand_scan_store(int cb, int cnt, int kA, int k
     }
 }
 
-template <int CPT>
+template <int TH, int CPT>
 __device__ __forceinline__ void zero_own(int *own) {
     int4 *own4 = reinterpret_cast<int4 *>(own);
     const int4 z = make_int4(0, 0, 0, 0);
+#if APS_OWN_PAD
+    constexpr int NV = APS_OWN_WORDS(TH * CPT) / 4;  // consecutive threads, consecutive vectors
+#pragma unroll
+    for (int m = 0; m < (NV + TH - 1) / TH; ++m)
+        if (m * TH + (int)threadIdx.x < NV) own4[m * TH + threadIdx.x] = z;
+#else
 #pragma unroll
     for (int m = 0; m < CPT / 4; ++m) own4[threadIdx.x * (CPT / 4) + m] = z;
+#endif
 }
 
 // general (rare) path: any number of children, clipped chunk by chunk. khi: inclusive child
@@ -601,13 +631,13 @@ __device__ __noinline__ void expand_tile_general(const int *khi, int klo0, int k
     for (int cb = kA & ~3; cb < kB; cb += CAP) {
         const int cnt = (kB - cb) < CAP ? (kB - cb) : CAP;
         __syncthreads();
-        zero_own<CPT>(own);
+        zero_own<TH, CPT>(own);
         __syncthreads();
         int klo = klo0;
         for (int j = 0; j < IPT; ++j) {
             const int kh = khi[j];
             const int lo_rel = klo - cb, hi_rel = kh - cb;
-            if (kh > klo && hi_rel > 0 && lo_rel < cnt) own[lo_rel > 0 ? lo_rel : 0] = tid * IPT + j + 1;
+            if (kh > klo && hi_rel > 0 && lo_rel < cnt) own[own_idx(lo_rel > 0 ? lo_rel : 0)] = tid * IPT + j + 1;
             klo = kh;
         }
         __syncthreads();
@@ -644,7 +674,7 @@ __device__ __forceinline__ int children_below_fast(u64 C, u64 Q, int n, double r
 // i.e. 16 consecutive weights -- free of bank conflicts. Rows past the end of the tensor are
 // zero-filled by the hardware, so ragged tails need no special case.
 #define APS_TILE_BYTES (APS_TILE * 8)
-#define APS_K3_DYN_SMEM (APS_TILE_BYTES + APS_K3_CAP * 4)
+#define APS_K3_DYN_SMEM (APS_TILE_BYTES + APS_OWN_WORDS(APS_K3_CAP) * 4)
 template <int KIND, bool MULTI>
 __global__ void __launch_bounds__(APS_K3_THREADS, MULTI ? APS_K3_MINBLOCKS - 2 : APS_K3_MINBLOCKS) k_resample(const __grid_constant__ DevCtx c, const long long s,
                                                              int32_t *__restrict__ anc_out,
@@ -693,23 +723,25 @@ __global__ void __launch_bounds__(APS_K3_THREADS, MULTI ? APS_K3_MINBLOCKS - 2 :
         }
         load_plan();
     }
-    if (tid == 0) {
+    if (tid == 0) {  // only warp 0 touches the mbarrier (init, TMA issue, wait): no block barrier needed here
         if (smem_u32(tilebuf) & 1023u) __trap();  // the 128-byte swizzle pattern assumes a 1 KB aligned tile
         mbar_init(&mbar, 1);
-    }
-    __syncthreads();
-    if (tid == 0) {
         mbar_expect_tx(&mbar, APS_TILE_BYTES);
         tma_load_2d(tilebuf, &tmap_q, &mbar, 0, (int)(base / APS_ROW));
         // pull the tile that a block ~2 residency waves later will need from HBM into L2 now
-        const long long pf = (long long)blockIdx.x + 2LL * APS_K3_MINBLOCKS * 148;
+#if APS_K3_PF_WAVES > 0
+        const long long pf = (long long)blockIdx.x + (long long)APS_K3_PF_WAVES * APS_K3_MINBLOCKS * 148;
         if (pf < (long long)gridDim.x) tma_prefetch_2d(&tmap_q, 0, (int)(pf * (APS_TILE / APS_ROW)));
+#endif
     }
     const u64 step = (u64)(s + c.ctr_offset);
     u64 tprefix = c.tile_prefix[blockIdx.x];
 
-    zero_own<APS_K3_CPT>(own);
-    if (tid < 32) mbar_wait(&mbar, 0);  // one warp polls the mbarrier, the others park on the block barrier
+    zero_own<APS_K3_THREADS, APS_K3_CPT>(own);
+    if (tid < 32) {  // one warp polls the mbarrier, the others park on the block barrier
+        __syncwarp();
+        mbar_wait(&mbar, 0);
+    }
     __syncthreads();
 
     // ---- this thread's APS_K3_IPT consecutive integer weights (its part of one 128-byte row of the
@@ -778,7 +810,7 @@ __global__ void __launch_bounds__(APS_K3_THREADS, MULTI ? APS_K3_MINBLOCKS - 2 :
 #pragma unroll
         for (int r = 0; r < APS_K3_IPT; ++r) {
             const int k = children_below_fast<KIND>(excl + cum[r], Q, n, ratio, roff, guard, key, step, &unsafe);
-            if (k > klo) own[klo - cb] = tid * APS_K3_IPT + r + 1;
+            if (k > klo) own[own_idx(klo - cb)] = tid * APS_K3_IPT + r + 1;
             klo = k;
         }
     }
@@ -793,11 +825,11 @@ __global__ void __launch_bounds__(APS_K3_THREADS, MULTI ? APS_K3_MINBLOCKS - 2 :
         int klx = tid == 0 ? kAx : children_below_checked<KIND>(excl, Q, R, n, ratio, roff, guard, key, step);
         const int cbx = kAx & ~3;
         if (kBx - cbx <= APS_K3_CAP) {
-            zero_own<APS_K3_CPT>(own);  // every thread is past the marker loop (the __syncthreads_or above)
+            zero_own<APS_K3_THREADS, APS_K3_CPT>(own);  // every thread is past the marker loop (the __syncthreads_or above)
             __syncthreads();
             for (int r = 0; r < APS_K3_IPT; ++r) {
                 const int k = children_below_checked<KIND>(excl + cum[r], Q, R, n, ratio, roff, guard, key, step);
-                if (k > klx) own[klx - cbx] = tid * APS_K3_IPT + r + 1;
+                if (k > klx) own[own_idx(klx - cbx)] = tid * APS_K3_IPT + r + 1;
                 klx = k;
             }
             __syncthreads();
@@ -949,7 +981,7 @@ __global__ void __launch_bounds__(APS_THREADS) k_expand_counts(const __grid_cons
                                                                const int identity_if_not_resampled,
                                                                const __grid_constant__ DevCtx c) {
     __shared__ u64 red[APS_WARPS];
-    __shared__ __align__(16) int own[APS_CAP];
+    __shared__ __align__(16) int own[APS_OWN_WORDS(APS_CAP)];
     __shared__ int wmax[APS_WARPS];
     const int tid = threadIdx.x;
     const long long base = (long long)blockIdx.x * APS_TILE;
@@ -1454,6 +1486,17 @@ __global__ void __launch_bounds__(APS_THREADS) k_to_one_based(const int32_t *__r
     for (long long i = (long long)blockIdx.x * APS_THREADS + threadIdx.x; i < n;
          i += (long long)gridDim.x * APS_THREADS)
         out[i] = (long long)in[i] + 1;
+}
+
+// second half of the L2 flush of aps_bench_resample: streaming reads replace the dirty lines the
+// memset left in L2 by clean ones, so the timed kernel does not pay for their write-back
+__global__ void __launch_bounds__(APS_K1_THREADS) k_read_flush(const uint4 *__restrict__ buf, long long n16, unsigned *sink) {
+    unsigned acc = 0;
+    for (long long i = (long long)blockIdx.x * APS_K1_THREADS + threadIdx.x; i < n16; i += (long long)gridDim.x * APS_K1_THREADS) {
+        const uint4 v = __ldcs(buf + i);
+        acc ^= v.x ^ v.y ^ v.z ^ v.w;
+    }
+    if (acc == 0x9E3779B9u) *sink = acc;
 }
 
 // synthetic integer weights for aps_bench_resample (hash of the index, roughly log-normal spread)

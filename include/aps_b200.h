@@ -126,7 +126,7 @@ int aps_randcat(const double *w, int64_t n, uint64_t key, uint64_t ctr, int64_t 
 
 /* ---- measurement helper: times the dominant resample kernel alone (reads N integer weights,
  *      writes N int32 ancestors) with CUDA events on its stream, L2 flushed between launches.   */
-int aps_bench_resample(int kind, int64_t n, int iters, int flush_l2, uint64_t seed,
+int aps_bench_resample(int kind, int64_t n, int iters, int flush_l2 /* 0 none, 1 write, 2 write + read-back (clean) */, uint64_t seed,
                        float *avg_ms_out, float *min_ms_out);
 
 /* ---- multi-GPU plumbing (one process per GPU; the host exchanges these opaque blobs with

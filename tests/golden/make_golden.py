@@ -26,6 +26,8 @@ CASES = {
     "lg1_c1_smc_systematic": ("linear_gaussian", 1000, 50, "SMC", "SYSTEMATIC", None, 1234, 0xDA7A0001, False),
     "lg1_smc_ess_half": ("linear_gaussian", 3001, 20, "SMC", "SYSTEMATIC", 0.5, 7, 0xDA7A0001, False),
     "lg1_smc_stratified": ("linear_gaussian", 2500, 12, "SMC", "STRATIFIED", None, 8, 0xDA7A0001, False),
+    "lg1_smc_multinomial": ("linear_gaussian", 2304, 10, "SMC", "MULTINOMIAL", None, 11, 0xDA7A0001, False),
+    "lg1_smc_residual_ess": ("linear_gaussian", 2304, 10, "SMC", "RESIDUAL", 0.5, 12, 0xDA7A0001, False),
     "lg4_pg_conditional": ("lg4", 4000, 10, "PG", "SYSTEMATIC", 0.5, 9, 0xDA7A0003, True),
     "sv_pgas_conditional": ("stochastic_volatility", 2048, 16, "PGAS", "SYSTEMATIC", 1.0, 10, 0xDA7A0004, True),
 }
