@@ -36,30 +36,40 @@ typedef void (*prop_fn)(const DevCtx, const long long, double *, const double *,
 typedef void (*res_fn)(const DevCtx, const long long, int32_t *, const CUtensorMap);
 typedef void (*pgas_fn)(const DevCtx, const long long, const double *, const int32_t *, int32_t *);
 
-template <int D, int OBS>
+template <int D, int OBS, bool MULTI>
 static prop_fn prop_for_dy(int dy) {
     switch (dy) {
-        case 1: return k_propagate<D, 1, OBS>;
-        case 2: return k_propagate<D, 2, OBS>;
-        case 3: return k_propagate<D, 3, OBS>;
-        default: return k_propagate<D, 4, OBS>;
+        case 1: return k_propagate<D, 1, OBS, MULTI>;
+        case 2: return k_propagate<D, 2, OBS, MULTI>;
+        case 3: return k_propagate<D, 3, OBS, MULTI>;
+        default: return k_propagate<D, 4, OBS, MULTI>;
     }
 }
-template <int OBS>
+template <int OBS, bool MULTI>
 static prop_fn prop_for_dim(int d, int dy) {
     switch (d) {
-        case 1: return prop_for_dy<1, OBS>(dy);
-        case 2: return prop_for_dy<2, OBS>(dy);
-        case 3: return prop_for_dy<3, OBS>(dy);
-        default: return prop_for_dy<4, OBS>(dy);
+        case 1: return prop_for_dy<1, OBS, MULTI>(dy);
+        case 2: return prop_for_dy<2, OBS, MULTI>(dy);
+        case 3: return prop_for_dy<3, OBS, MULTI>(dy);
+        default: return prop_for_dy<4, OBS, MULTI>(dy);
     }
 }
-static prop_fn pick_propagate(int obs, int d, int dy) {
+template <bool MULTI>
+static prop_fn pick_propagate_m(int obs, int d, int dy) {
     switch (obs) {
-        case APS_OBS_LINEAR_GAUSS: return prop_for_dim<APS_OBS_LINEAR_GAUSS>(d, dy);
-        case APS_OBS_STOCH_VOL: return prop_for_dim<APS_OBS_STOCH_VOL>(d, 1);
-        default: return prop_for_dim<APS_OBS_CONST>(d, 1);
+        case APS_OBS_LINEAR_GAUSS: return prop_for_dim<APS_OBS_LINEAR_GAUSS, MULTI>(d, dy);
+        case APS_OBS_STOCH_VOL: return k_propagate<1, 1, APS_OBS_STOCH_VOL, MULTI>;  // d = dy = 1 (aps_model_prepare)
+        default:  // constant log-likelihood: dy is not used
+            switch (d) {
+                case 1: return k_propagate<1, 1, APS_OBS_CONST, MULTI>;
+                case 2: return k_propagate<2, 1, APS_OBS_CONST, MULTI>;
+                case 3: return k_propagate<3, 1, APS_OBS_CONST, MULTI>;
+                default: return k_propagate<4, 1, APS_OBS_CONST, MULTI>;
+            }
     }
+}
+static prop_fn pick_propagate(int obs, int d, int dy, bool multi) {
+    return multi ? pick_propagate_m<true>(obs, d, dy) : pick_propagate_m<false>(obs, d, dy);
 }
 static pgas_fn pick_pgas_max(int d) {
     switch (d) {
@@ -148,8 +158,20 @@ static void preload_kernels() {
     cudaFuncGetAttributes(&a, k_weights_out);
     cudaFuncGetAttributes(&a, k_init_sweep);
     cudaFuncGetAttributes(&a, k_plan_multi);
+    cudaFuncGetAttributes(&a, k_fill_fat);
     cudaGetLastError();
     done = true;
+}
+
+// children from which a parent is deferred to the fat list: well above what one expand pass holds,
+// and at least Ng / 128 so that a list never exceeds APS_FAT_MAX entries (APS_FAT_MIN: test override)
+static int fat_min_for(long long n_global) {
+    long long m = (n_global + APS_FAT_MAX - 1) / APS_FAT_MAX;
+    long long want = 16LL * APS_K3_CAP;
+    if (const char *e = getenv("APS_FAT_MIN")) want = atoll(e);
+    if (m < want) m = want;
+    if (m < 8) m = 8;
+    return (int)(m > 2147483647LL ? 2147483647LL : m);
 }
 
 static int g_sm_count = 0;
@@ -319,11 +341,14 @@ extern "C" int aps_create(const aps_config *cfg, aps_handle **out) {
     CUH(cudaMalloc(&h->d_traj, sizeof(double) * (size_t)T * d));
     CUH(cudaMalloc(&h->d_Y, sizeof(double) * (size_t)T * c.dy));
     CUH(cudaMalloc(&h->d_scratch, sizeof(double) * (size_t)Nl * d));
-    if (world > 1) {
-        CUH(cudaMalloc(&h->d_mail, sizeof(MailSlot) * APS_MAIL_KINDS * APS_MAX_RANKS));
-        CUH(cudaMemset(h->d_mail, 0, sizeof(MailSlot) * APS_MAIL_KINDS * APS_MAX_RANKS));
-        CUH(cudaMalloc(&h->d_peers, sizeof(PeerTable)));
-    }
+    // mailbox + fat-parent lists in one allocation (one IPC handle covers both)
+    c.fat_steps = T + 2;
+    CUH(cudaMalloc(&h->d_mail, aps_mailbox_alloc_bytes(c.fat_steps)));
+    CUH(cudaMemset(h->d_mail, 0, aps_mailbox_alloc_bytes(c.fat_steps)));
+    c.fat_cnt = reinterpret_cast<int *>(reinterpret_cast<char *>(h->d_mail) + aps_mail_bytes());
+    c.fat = reinterpret_cast<FatEntry *>(reinterpret_cast<char *>(h->d_mail) + aps_mail_bytes() + aps_fatcnt_bytes(c.fat_steps));
+    c.fat_min = fat_min_for(N);
+    if (world > 1) CUH(cudaMalloc(&h->d_peers, sizeof(PeerTable)));
     if (cfg->resampler == APS_RESAMPLE_MULTINOMIAL || cfg->resampler == APS_RESAMPLE_RESIDUAL) {
         CUH(cudaMalloc(&h->d_cum, sizeof(u64) * (size_t)c.NS));
         CUH(cudaMalloc(&h->d_counts, sizeof(int) * (size_t)c.NS));
@@ -345,7 +370,7 @@ extern "C" int aps_create(const aps_config *cfg, aps_handle **out) {
     c.Y = h->d_Y;
     c.ref = h->d_ref;
     c.sp = h->d_sp;
-    h->f_prop = pick_propagate(cfg->model.obs_kind, d, cfg->model.dy);
+    h->f_prop = pick_propagate(cfg->model.obs_kind, d, cfg->model.dy, world > 1);
     prefer_max_smem(h->f_prop);
     h->f_res = pick_resample(cfg->resampler, world > 1);
     h->f_pmax = pick_pgas_max(d);
@@ -406,6 +431,7 @@ static long long enqueue_sweep(aps_handle *h, LaunchProf *prof = nullptr) {
         ++n;                             \
     } while (0)
     cudaMemsetAsync(c.acc, 0, sizeof(StepAcc) * (size_t)(c.T + 2), st);
+    cudaMemsetAsync(c.fat_cnt, 0, sizeof(int) * (size_t)c.fat_steps, st);
     if (h->d_rs) {
         cudaMemsetAsync(h->d_rs, 0, sizeof(ResidualState) * (size_t)(c.T + 2), st);
         cudaMemsetAsync(h->d_done2, 0, sizeof(unsigned) * (size_t)(c.T + 2), st);
@@ -473,13 +499,17 @@ static long long enqueue_sweep(aps_handle *h, LaunchProf *prof = nullptr) {
             const int gs = stride_grid((c.Ng + 1) / 2);
             APS_LAUNCH(2, k_multi_search<1><<<gs, APS_K1_THREADS, 0, st>>>(a, &h->d_sp->key));
             APS_LAUNCH(2, k_scan_tile_counts<<<1, APS_THREADS, 0, st>>>(a, nullptr, c, t));
-            APS_LAUNCH(2, k_expand_counts<<<gt, APS_THREADS, 0, st>>>(a, anc_slab(t), 1, c));
+            APS_LAUNCH(2, k_expand_counts<<<gt, APS_THREADS, 0, st>>>(a, anc_slab(t), 1, c, t));
         }
         if (c.sampler == APS_PGAS && t >= 2 && t <= c.T - 1) {
             APS_LAUNCH(3, h->f_pmax<<<gp, APS_K1_THREADS, 0, st>>>(c, t, x_slab(t - 1), anc_slab(t - 1), anc_slab(t)));
             APS_LAUNCH(3, h->f_psel<<<gt, APS_THREADS, 0, st>>>(c, t, x_slab(t - 1), anc_slab(t - 1), anc_slab(t)));
         }
     }
+    // children of fat parents at the final decision point (no propagate kernel follows to resolve them)
+    // (sharded: every block spins on the peers first, so the grid stays small -- ranks emulated on one
+    // GPU must all fit at once; the fill itself is a few MB at most, once per sweep)
+    APS_LAUNCH(2, k_fill_fat<<<c.world > 1 ? 16 : sm_count() * 2, APS_K1_THREADS, 0, st>>>(c, c.T, anc_slab(c.T), 1));
 #undef APS_LAUNCH
     return n;
 }
@@ -699,6 +729,14 @@ extern "C" int aps_get_ancestors(aps_handle *h, int64_t t, int32_t *anc_out) {
     return APS_OK;
 }
 
+extern "C" int aps_get_fat_counts(aps_handle *h, int32_t *counts_out) {
+    NEED_SWEEP("aps_get_fat_counts");
+    if (!counts_out) return fail(APS_ERR_INVALID, "aps_get_fat_counts: null output");
+    CU(cudaMemcpyAsync(counts_out, h->ctx.fat_cnt, sizeof(int) * (size_t)(h->ctx.T + 1), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return APS_OK;
+}
+
 extern "C" int aps_last_sweep_ms(aps_handle *h, float *ms_out) {
     NEED_SWEEP("aps_last_sweep_ms");
     if (ms_out) *ms_out = h->last_ms;
@@ -731,6 +769,8 @@ struct OpWorkspace {
     int *d_err = nullptr;
     SweepState *st = nullptr;
     SweepParams *sp = nullptr;
+    int *d_fat_cnt = nullptr;     // fat-parent list of the one decision point an operator call has
+    FatEntry *d_fat = nullptr;
 };
 static OpWorkspace g_ws;
 
@@ -743,6 +783,8 @@ static int ws_reserve(OpWorkspace &w, long long m, long long n) {
         CU(cudaMalloc(&w.d_err, sizeof(int)));
         CU(cudaMalloc(&w.st, sizeof(SweepState)));
         CU(cudaMalloc(&w.sp, sizeof(SweepParams)));
+        CU(cudaMalloc(&w.d_fat_cnt, 16));
+        CU(cudaMalloc(&w.d_fat, sizeof(FatEntry) * APS_FAT_MAX));
         CU(cudaMalloc(&w.d_rs, sizeof(ResidualState)));
         CU(cudaMalloc(&w.d_done2, sizeof(unsigned)));
     }
@@ -813,6 +855,10 @@ static void op_ctx(OpWorkspace &w, DevCtx &c, long long m, long long n_draw) {
     c.ess_threshold = NAN;
     c.logN = 0.0;
     c.n_override = n_draw;
+    c.fat_cnt = w.d_fat_cnt;
+    c.fat = w.d_fat;
+    c.fat_steps = 1;
+    c.fat_min = fat_min_for(n_draw > m ? n_draw : m);
 }
 
 // max + normalise of a weight / log-weight vector into the workspace; fills *plan_host
@@ -830,6 +876,7 @@ static int op_normalise(OpWorkspace &w, DevCtx &c, const double *in, long long m
     sp.pad = 0;
     CU(cudaMemcpyAsync(w.sp, &sp, sizeof(sp), cudaMemcpyHostToDevice, w.stream));
     CU(cudaMemsetAsync(w.acc, 0, sizeof(StepAcc), w.stream));
+    CU(cudaMemsetAsync(w.d_fat_cnt, 0, 16, w.stream));
     if (c.NS > m) CU(cudaMemsetAsync(w.d_q + m, 0, sizeof(u64) * (size_t)(c.NS - m), w.stream));  // zero-weight padding
     k_vector_max<INPUT><<<stride_grid(m), APS_K1_THREADS, 0, w.stream>>>(d_in, m, w.acc);
     c.ctr_offset = (long long)ctr;
@@ -865,6 +912,7 @@ extern "C" int aps_resample(int kind, const double *wts, int64_t m, int64_t n, u
         rc = enable_k3_smem();
         if (rc) return rc;
         pick_resample(kind)<<<(int)c.num_tiles, APS_K3_THREADS, APS_K3_DYN_SMEM, w.stream>>>(c, 0, w.d_idx32, w.tmap_q);
+        k_fill_fat<<<sm_count() * 2, APS_K1_THREADS, 0, w.stream>>>(c, 0, w.d_idx32, 0);
     } else {
         const int gt = (int)c.num_tiles;
         MultiArgs a;
@@ -893,7 +941,8 @@ extern "C" int aps_resample(int kind, const double *wts, int64_t m, int64_t n, u
             a.out_offset = &w.d_rs->n_det;
             k_residual_split<<<gt, APS_THREADS, 0, w.stream>>>(a, w.d_q, w.d_rq, w.d_rs);
             k_scan_tile_counts<<<1, APS_THREADS, 0, w.stream>>>(a, nullptr, c, 0);
-            k_expand_counts<<<gt, APS_THREADS, 0, w.stream>>>(a, w.d_idx32, 0, c);
+            k_expand_counts<<<gt, APS_THREADS, 0, w.stream>>>(a, w.d_idx32, 0, c, 0);
+            k_fill_fat<<<sm_count() * 2, APS_K1_THREADS, 0, w.stream>>>(c, 0, w.d_idx32, 0);
             a.wplan = w.plan2;
             k_residual_weights<<<gt, APS_THREADS, 0, w.stream>>>(a, w.d_rq, w.d_rs, w.tile_sum, w.tile_prefix, w.plan2,
                                                                 w.d_done2, w.d_err);
@@ -1024,6 +1073,7 @@ extern "C" int aps_bench_resample(int kind, int64_t n, int iters, int flush_l2, 
     sp.pad = 0;
     CU(cudaMemcpyAsync(w.sp, &sp, sizeof(sp), cudaMemcpyHostToDevice, w.stream));
     CU(cudaMemsetAsync(w.acc, 0, sizeof(StepAcc), w.stream));
+    CU(cudaMemsetAsync(w.d_fat_cnt, 0, 16, w.stream));
     if (c.NS > n) CU(cudaMemsetAsync(w.d_q + n, 0, sizeof(u64) * (size_t)(c.NS - n), w.stream));
     k_bench_weights<<<stride_grid(n), APS_THREADS, 0, w.stream>>>(w.d_q, n, c.S, seed);
     k_normalise<IN_Q><<<(int)c.num_tiles, APS_K2_THREADS, 0, w.stream>>>(c, nullptr, 0);

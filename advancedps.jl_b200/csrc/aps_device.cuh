@@ -67,6 +67,38 @@ struct PeerTable {
     MailSlot *mail[APS_MAX_RANKS];  // mail[r][kind * APS_MAX_RANKS + src]
 };
 
+// Fat parents. Under weight degeneracy a single parent can own a large share of all children; the
+// block that owns its tile would have to write them all (O(children) serial chunks). Instead,
+// parents with at least fat_min children are recorded as (child range, parent) entries in a small
+// per-decision-point list that lives next to the mailbox (so peers can push into it), their child
+// range is skipped by the expand, and the consumer fills it in: the propagate kernel of the next
+// step resolves its own slots against the list and patches the ancestor store; k_fill_fat does the
+// same after the final decision point and at the operator level. fat_min >= Ng / 128, so a list
+// never holds more than APS_FAT_MAX entries.
+#define APS_FAT_MAX 128
+struct FatEntry {
+    int lo, hi;   // global child slots [lo, hi)
+    int parent;   // global parent index
+    int pad;
+};
+// byte layout of the mailbox allocation: MailSlot[KINDS * RANKS] | int fat_cnt[steps] | FatEntry[steps][APS_FAT_MAX]
+__host__ __device__ __forceinline__ size_t aps_mail_bytes() { return sizeof(MailSlot) * APS_MAIL_KINDS * APS_MAX_RANKS; }
+__host__ __device__ __forceinline__ size_t aps_fatcnt_bytes(long long steps) { return ((size_t)steps * sizeof(int) + 15) & ~(size_t)15; }
+__host__ __device__ __forceinline__ size_t aps_mailbox_alloc_bytes(long long steps) {
+    return aps_mail_bytes() + aps_fatcnt_bytes(steps) + (size_t)steps * APS_FAT_MAX * sizeof(FatEntry);
+}
+
+// parent of global child slot g if it lies in a deferred range, else -1
+__device__ __forceinline__ int fat_lookup(const FatEntry *ent, int nfat, int g) {
+    int a = -1;
+#pragma unroll 1
+    for (int e = 0; e < nfat; ++e) {
+        const int4 v = __ldg(reinterpret_cast<const int4 *>(ent + e));
+        if (g >= v.x && g < v.y) a = v.z;
+    }
+    return a;
+}
+
 __device__ __forceinline__ u64 ld_sys_u64(const u64 *p) {
     u64 v;
     asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");

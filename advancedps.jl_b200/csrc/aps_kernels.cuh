@@ -51,6 +51,10 @@ struct DevCtx {
     const PeerTable *peers; // device copy of the peer table, or null on one GPU
     int rank, world;
     int dbg, pad2;         // diagnostics only (APS_DEBUG_MULTI): 1 skip waits, 2 skip sys fences, 4 local gathers, 8 local scatter
+    int *fat_cnt;          // [steps] entries in the fat-parent list of each decision point
+    FatEntry *fat;         // [steps][APS_FAT_MAX]
+    long long fat_steps;   // steps the lists are sized for (T + 2; 1 at the operator level)
+    int fat_min, pad3;     // children from which a parent is deferred to the consumer
     long long n_override;  // operator level: number of indices to draw (0: N, or N-1 with a reference)
     long long ctr_offset;  // operator level: Philox step counter = plan index + ctr_offset
 };
@@ -87,10 +91,10 @@ __global__ void k_init_sweep(const __grid_constant__ DevCtx c) {
 // One thread per PAIR of adjacent slots (2p, 2p+1): the pair shares D Philox blocks and their
 // Box-Muller normals (aps_pair_normals), ancestors / log-weights / states move as 8- and 16-byte
 // vectors. Block maxima of the new log-weights are folded into one atomicMax per block.
-template <int D, int DY, int OBS>
+template <int D, int DY, int OBS, bool MULTI>
 __global__ void __launch_bounds__(APS_K1_THREADS) k_propagate(const __grid_constant__ DevCtx c, const long long t,
                                                            double *__restrict__ xt, const double *__restrict__ xp,
-                                                           const int32_t *__restrict__ anc) {
+                                                           const int32_t *anc) {  // not __restrict__: patched below
     __shared__ u64 red[APS_K1_THREADS / 32];
     SpanProbe probe(&c.acc[t], 0, c.dbg & 16);
     const long long N = c.N, NS = c.NS;
@@ -105,14 +109,37 @@ __global__ void __launch_bounds__(APS_K1_THREADS) k_propagate(const __grid_const
     unsigned bad = 0;
     const long long npairs = (N + 1) >> 1;
     const long long pair0 = c.slot0 >> 1;
-    const bool multi = c.world > 1;
+    const bool multi = MULTI;
     const u64 seq0 = multi ? c.sp->epoch * (u64)(c.T + 2) : 0ull;
     const long long xoff = xp - c.x;  // slab offset, identical on every rank
-    // the normals do not depend on the ancestors: draw the first pair's before waiting for the peers
     long long p = (long long)blockIdx.x * APS_K1_THREADS + threadIdx.x;
+    // Children of fat parents (deferred by the resample kernel): every thread first resolves its
+    // OWN slots against the list and patches the ancestor store, then runs the unchanged main loop
+    // (a separate pre-pass keeps the lookup out of the main loop's register budget).
+    auto resolve_fat = [&]() {
+        if (t <= 1) return;
+        int nfat = c.fat_cnt[t - 1];
+        if (!nfat) return;
+        if (nfat > APS_FAT_MAX) nfat = APS_FAT_MAX;
+        const FatEntry *fatl = c.fat + (t - 1) * APS_FAT_MAX;
+        int32_t *ancw = const_cast<int32_t *>(anc);
+#pragma unroll 1
+        for (long long pp = p; pp < npairs; pp += (long long)gridDim.x * APS_K1_THREADS) {
+#pragma unroll 1
+            for (int h = 0; h < 2; ++h) {
+                const long long i = 2 * pp + h;
+                if (i < N) {
+                    const int af = fat_lookup(fatl, nfat, (int)(c.slot0 + i));
+                    if (af >= 0) ancw[i] = af;
+                }
+            }
+        }
+    };
+    if (!MULTI) resolve_fat();
+    // the normals do not depend on the ancestors: draw the first pair's before waiting for the peers
     double z[2 * D];
     if (p < npairs) aps_pair_normals<D>(key, (u64)(pair0 + p), (u64)t, z);
-    if (multi) {
+    if (MULTI) {
         // the ancestor scatter of step t-1 (peer stores from every rank) must have landed: this
         // rank's resample kernel is complete (stream order), so block 0 tells every rank, and
         // every block waits until all ranks said so. At t = 1 the same exchange makes sure every
@@ -124,6 +151,7 @@ __global__ void __launch_bounds__(APS_K1_THREADS) k_propagate(const __grid_const
         if (!(c.dbg & 1) && !mail_wait(c.peers, c.rank, c.world, 2, seq0 + (u64)(t - 1) + 1, s_w, 1, c.st->spin))
             c.st->err = APS_ERR_COMM;
         __syncthreads();
+        resolve_fat();  // the peers' pushes into this rank's list are complete now
     }
     for (bool first = true; p < npairs; p += (long long)gridDim.x * APS_K1_THREADS, first = false) {
         if (!first) aps_pair_normals<D>(key, (u64)(pair0 + p), (u64)t, z);
@@ -520,6 +548,48 @@ struct AncDst {
     }
 };
 
+// ---- fat parents (see aps_device.cuh)
+struct FatSink {
+    int *cnt;                // this rank's counter of decision point s
+    FatEntry *ent;           // this rank's entries of decision point s
+    const PeerTable *peers;  // null on one GPU
+    size_t off_cnt, off_ent; // byte offsets of (cnt, ent) from the mailbox base, for the peers' copies
+    int fat_min, nl, rank, pad;
+};
+__device__ __forceinline__ FatSink make_fat_sink(const DevCtx &c, long long s, bool multi) {
+    FatSink f;
+    f.cnt = c.fat_cnt + s;
+    f.ent = c.fat + s * APS_FAT_MAX;
+    f.peers = multi ? c.peers : nullptr;
+    f.off_cnt = aps_mail_bytes() + (size_t)s * sizeof(int);
+    f.off_ent = aps_mail_bytes() + aps_fatcnt_bytes(c.fat_steps) + (size_t)s * APS_FAT_MAX * sizeof(FatEntry);
+    f.fat_min = c.fat_min;
+    f.nl = (int)c.N;
+    f.rank = c.rank;
+    f.pad = 0;
+    return f;
+}
+// record parent `parent` as the owner of the global child slots [lo, hi) on every rank that owns some of them
+__device__ __forceinline__ void fat_push(const FatSink &f, int lo, int hi, int parent) {
+    FatEntry e;
+    e.lo = lo;
+    e.hi = hi;
+    e.parent = parent;
+    e.pad = 0;
+    if (!f.peers) {
+        const int idx = atomicAdd(f.cnt, 1);
+        if (idx < APS_FAT_MAX) f.ent[idx] = e;
+        return;
+    }
+    const int r0 = lo / f.nl, r1 = (hi - 1) / f.nl;
+    for (int r = r0; r <= r1; ++r) {
+        char *mb = reinterpret_cast<char *>(f.peers->mail[r]);
+        int *cnt = r == f.rank ? f.cnt : reinterpret_cast<int *>(mb + f.off_cnt);
+        FatEntry *ent = r == f.rank ? f.ent : reinterpret_cast<FatEntry *>(mb + f.off_ent);
+        const int idx = atomicAdd_system(cnt, 1);
+        if (idx < APS_FAT_MAX) *reinterpret_cast<int4 *>(ent + idx) = *reinterpret_cast<const int4 *>(&e);
+    }
+}
 // Marker array layout. Parents are thread-blocked (16 consecutive parents per thread), so in one
 // marker round the lanes of a warp write child positions about 16 apart: with a plain layout they
 // fall into two banks (16-way conflicts; ncu: 1/3 of all shared-memory wavefronts of the kernel).
@@ -622,15 +692,41 @@ __device__ __forceinline__ void zero_own(int *own) {
 }
 
 // general (rare) path: any number of children, clipped chunk by chunk. khi: inclusive child
-// counts of this thread's parents, klo0: count below its first parent.
+// counts of this thread's parents, klo0: count below its first parent. Parents with at least
+// fat_min children are pushed to the fat list and their child range is skipped (the consumer
+// fills it in), so the cost follows the number of parents, not the number of children.
 template <int TH, int IPT, int CPT>
 __device__ __noinline__ void expand_tile_general(const int *khi, int klo0, int kA, int kB, int base, const AncDst &dst,
-                                                 int *own, int *wmax) {
+                                                 int *own, int *wmax, const FatSink &fat) {
     constexpr int CAP = TH * CPT;
+    __shared__ int s_to;
     const int tid = threadIdx.x;
-    for (int cb = kA & ~3; cb < kB; cb += CAP) {
-        const int cnt = (kB - cb) < CAP ? (kB - cb) : CAP;
+    {
+        int klo = klo0;
+        for (int j = 0; j < IPT; ++j) {
+            const int kh = khi[j];
+            if (kh - klo >= fat.fat_min) fat_push(fat, klo, kh, base + tid * IPT + j);
+            klo = kh;
+        }
+    }
+    for (int cb = kA & ~3; cb < kB;) {
+        if (tid == 0) s_to = 0;
         __syncthreads();
+        {   // does this chunk start inside a deferred range? then continue behind it
+            int klo = klo0;
+            for (int j = 0; j < IPT; ++j) {
+                const int kh = khi[j];
+                if (kh - klo >= fat.fat_min && klo <= cb && (kh & ~3) > cb) s_to = kh & ~3;
+                klo = kh;
+            }
+        }
+        __syncthreads();
+        const int to = s_to;
+        if (to > cb) {
+            cb = to;
+            continue;
+        }
+        const int cnt = (kB - cb) < CAP ? (kB - cb) : CAP;
         zero_own<TH, CPT>(own);
         __syncthreads();
         int klo = klo0;
@@ -642,6 +738,7 @@ __device__ __noinline__ void expand_tile_general(const int *khi, int klo0, int k
         }
         __syncthreads();
         expand_scan_store<TH, CPT>(cb, cnt, kA, kB, base, dst, own, wmax);
+        cb += CAP;
     }
 }
 
@@ -838,7 +935,7 @@ __global__ void __launch_bounds__(APS_K3_THREADS, MULTI ? APS_K3_MINBLOCKS - 2 :
             int khi[APS_K3_IPT];
             for (int r = 0; r < APS_K3_IPT; ++r)
                 khi[r] = children_below_checked<KIND>(excl + cum[r], Q, R, n, ratio, roff, guard, key, step);
-            expand_tile_general<APS_K3_THREADS, APS_K3_IPT, APS_K3_CPT>(khi, klx, kAx, kBx, gbase, dst, own, wmax);
+            expand_tile_general<APS_K3_THREADS, APS_K3_IPT, APS_K3_CPT>(khi, klx, kAx, kBx, gbase, dst, own, wmax, make_fat_sink(c, s, MULTI));
         }
     }
 
@@ -979,7 +1076,7 @@ __global__ void __launch_bounds__(APS_THREADS) k_scan_tile_counts(const __grid_c
 // parent ids and child slots are global, children are scattered to the rank that owns their slot.
 __global__ void __launch_bounds__(APS_THREADS) k_expand_counts(const __grid_constant__ MultiArgs a, int32_t *__restrict__ anc_out,
                                                                const int identity_if_not_resampled,
-                                                               const __grid_constant__ DevCtx c) {
+                                                               const __grid_constant__ DevCtx c, const long long fat_step) {
     __shared__ u64 red[APS_WARPS];
     __shared__ __align__(16) int own[APS_OWN_WORDS(APS_CAP)];
     __shared__ int wmax[APS_WARPS];
@@ -1015,7 +1112,7 @@ __global__ void __launch_bounds__(APS_THREADS) k_expand_counts(const __grid_cons
     dst.slab_off = multi ? anc_out - c.anc : 0;
     dst.nl = (int)a.N;
     dst.lo = (int)slot0;
-    expand_tile_general<APS_THREADS, APS_IPT, APS_CPT>(khi, excl, kA, kB, (int)(slot0 + base), dst, own, wmax);
+    expand_tile_general<APS_THREADS, APS_IPT, APS_CPT>(khi, excl, kA, kB, (int)(slot0 + base), dst, own, wmax, make_fat_sink(c, fat_step, multi));
     const long long n = a.plan->n;
     if (identity_if_not_resampled && blockIdx.x == gridDim.x - 1 && tid == 0) {  // reference particle: globally last slot
         if (!multi && n < a.N) anc_out[a.N - 1] = (int32_t)(a.N - 1);
@@ -1486,6 +1583,34 @@ __global__ void __launch_bounds__(APS_THREADS) k_to_one_based(const int32_t *__r
     for (long long i = (long long)blockIdx.x * APS_THREADS + threadIdx.x; i < n;
          i += (long long)gridDim.x * APS_THREADS)
         out[i] = (long long)in[i] + 1;
+}
+
+// fills the deferred child ranges of decision point s into this rank's ancestor slab (after the
+// final decision point, where no propagate kernel follows, and at the operator level)
+__global__ void __launch_bounds__(APS_K1_THREADS) k_fill_fat(const __grid_constant__ DevCtx c, const long long s,
+                                                          int32_t *__restrict__ anc_out, const int barrier) {
+    if (barrier && c.world > 1) {
+        // sharded, after the final decision point: the peers' resample kernels (which push into this
+        // rank's list and scatter into its ancestor store) must be complete -- same exchange as the
+        // one at the start of k_propagate
+        __shared__ u64 s_w[APS_MAX_RANKS][4];
+        const u64 v0 = 0;
+        const u64 seq = c.sp->epoch * (u64)(c.T + 2) + (u64)s + 1;
+        if (blockIdx.x == 0) mail_post(c.peers, c.rank, c.world, 2, seq, &v0, 1);
+        if (!(c.dbg & 1) && !mail_wait(c.peers, c.rank, c.world, 2, seq, s_w, 1, nullptr)) c.st->err = APS_ERR_COMM;
+        __syncthreads();
+    }
+    int nfat = c.fat_cnt[s];
+    if (nfat > APS_FAT_MAX) nfat = APS_FAT_MAX;
+    // this rank's child slots (operator level: n_override children drawn from N weights)
+    const long long lo_r = c.slot0, hi_r = c.slot0 + (c.n_override > 0 ? c.n_override : c.N);
+    for (int e = 0; e < nfat; ++e) {
+        const FatEntry f = c.fat[s * APS_FAT_MAX + e];
+        const long long lo = f.lo > lo_r ? f.lo : lo_r, hi = f.hi < hi_r ? f.hi : hi_r;
+        for (long long g = lo + (long long)blockIdx.x * APS_K1_THREADS + threadIdx.x; g < hi;
+             g += (long long)gridDim.x * APS_K1_THREADS)
+            anc_out[g - lo_r] = f.parent;
+    }
 }
 
 // second half of the L2 flush of aps_bench_resample: streaming reads replace the dirty lines the

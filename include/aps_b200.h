@@ -95,6 +95,7 @@ int aps_sweep_profiled(aps_handle *h, uint64_t master_seed, const double *ref_tr
 /* rand(pc.rng, pc) + trajectory extraction (src/container.jl:33-36, src/smc.jl:127).
  * traj_out: T x d host doubles or NULL; index_out: 0-based slot in the final particle set.      */
 int aps_pick_trajectory(aps_handle *h, double *traj_out, int64_t *index_out);
+/* (sharded handles: a collective call; index_out is the GLOBAL slot, every rank gets the trajectory) */
 
 /* SMCSample fields (src/smc.jl:23-27,56) materialised lazily.                                  */
 int aps_get_weights(aps_handle *h, double *w_out /* N */);                 /* getweights, container.jl:95 */
@@ -107,6 +108,9 @@ int aps_get_step_stats(aps_handle *h, double *logz_out /* T */, double *ess_out 
  * build time t (2..T+1; T+1 = final resampled set) as N int32, 0-based.                         */
 int aps_get_states(aps_handle *h, int64_t t, double *x_out);
 int aps_get_ancestors(aps_handle *h, int64_t t, int32_t *anc_out);
+/* diagnostics: number of "fat" parents (children deferred to the consumer kernel)
+ * recorded on this rank at each decision point s = 0..T of the last sweep                        */
+int aps_get_fat_counts(aps_handle *h, int32_t *counts_out /* T+1 */);
 /* device time (ms, CUDA events on the handle's stream) of the last aps_sweep                    */
 int aps_last_sweep_ms(aps_handle *h, float *ms_out);
 /* kernels launched by the last aps_sweep (nodes of the replayed CUDA graph count one each)     */
