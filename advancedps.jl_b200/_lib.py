@@ -21,7 +21,7 @@ EXPORTS = [
     "aps_create", "aps_destroy", "aps_set_observations", "aps_sweep", "aps_sweep_profiled",
     "aps_pick_trajectory",
     "aps_get_weights", "aps_get_logweights", "aps_get_final_states", "aps_get_trajectory",
-    "aps_get_step_stats", "aps_get_states", "aps_get_ancestors", "aps_get_fat_counts", "aps_last_sweep_ms",
+    "aps_get_step_stats", "aps_get_states", "aps_get_ancestors", "aps_get_fat_counts", "aps_smoothing_mean", "aps_last_sweep_ms",
     "aps_last_sweep_launches", "aps_resample", "aps_logsumexp", "aps_softmax", "aps_ess",
     "aps_randcat", "aps_bench_resample", "aps_ipc_export", "aps_ipc_import", "aps_last_error",
     "aps_version",
@@ -180,6 +180,13 @@ class Handle:
         a = np.zeros(self.N, dtype=np.int32)
         check(lib().aps_get_ancestors(self._h, C.c_int64(t), ptr(a)))
         return a
+
+    def smoothing_mean(self):
+        """sum_i W_i X_i[t] for t = 1..T over the final weighted particle set (T x d); sharded
+        handles return this rank's partial sums."""
+        m = np.zeros((self.T, self.d))
+        check(lib().aps_smoothing_mean(self._h, ptr(m)))
+        return m
 
     def fat_counts(self):
         a = np.zeros(self.T + 1, dtype=np.int32)

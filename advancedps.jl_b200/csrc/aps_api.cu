@@ -159,6 +159,7 @@ static void preload_kernels() {
     cudaFuncGetAttributes(&a, k_init_sweep);
     cudaFuncGetAttributes(&a, k_plan_multi);
     cudaFuncGetAttributes(&a, k_fill_fat);
+    cudaFuncGetAttributes(&a, k_smooth_step);
     cudaGetLastError();
     done = true;
 }
@@ -726,6 +727,37 @@ extern "C" int aps_get_ancestors(aps_handle *h, int64_t t, int32_t *anc_out) {
     CU(cudaMemcpyAsync(anc_out, c.anc + ((t - 1) % c.anc_slabs) * c.NS, sizeof(int32_t) * (size_t)c.N,
                        cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
+    return APS_OK;
+}
+
+extern "C" int aps_smoothing_mean(aps_handle *h, double *mean_out) {
+    NEED_SWEEP("aps_smoothing_mean");
+    if (!mean_out) return fail(APS_ERR_INVALID, "aps_smoothing_mean: null output");
+    if (!h->cfg.keep_history) return fail(APS_ERR_INVALID, "aps_smoothing_mean: handle was created with keep_history = 0");
+    const DevCtx &c = h->ctx;
+    int res = 0;
+    int rc = final_resampled(h, &res);
+    if (rc) return rc;
+    // scratch: ancestor cursor per slot, block partials, per-step tickets, the T x d result
+    int32_t *d_idx = nullptr;
+    double *d_partial = nullptr, *d_mean = nullptr;
+    unsigned *d_ctr = nullptr;
+    CU(cudaMalloc(&d_idx, sizeof(int32_t) * (size_t)c.N));
+    CU(cudaMalloc(&d_partial, sizeof(double) * APS_SMOOTH_BLOCKS * APS_MAX_D));
+    CU(cudaMalloc(&d_mean, sizeof(double) * (size_t)c.T * c.d));
+    CU(cudaMalloc(&d_ctr, sizeof(unsigned) * (size_t)c.T));
+    CU(cudaMemsetAsync(d_ctr, 0, sizeof(unsigned) * (size_t)c.T, h->stream));
+    long long g = (c.N + APS_K1_THREADS - 1) / APS_K1_THREADS;
+    if (g > APS_SMOOTH_BLOCKS) g = APS_SMOOTH_BLOCKS;
+    for (long long t = c.T; t >= 1; --t)
+        k_smooth_step<<<(int)g, APS_K1_THREADS, 0, h->stream>>>(c, t, d_idx, c.q, res, d_partial, d_ctr, d_mean);
+    CU(cudaMemcpyAsync(mean_out, d_mean, sizeof(double) * (size_t)c.T * c.d, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    cudaFree(d_idx);
+    cudaFree(d_partial);
+    cudaFree(d_mean);
+    cudaFree(d_ctr);
+    CU(cudaGetLastError());
     return APS_OK;
 }
 

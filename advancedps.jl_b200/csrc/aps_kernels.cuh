@@ -306,18 +306,24 @@ __device__ __forceinline__ void record_plan(const DevCtx &c, long long s, const 
 // (q >> Hs) and (q >> Hs)^2. The last block to finish scans the tile totals and writes the plan
 // of decision point s: logZ, ESS, the resampling decision, the systematic offset, the evidence.
 // K2 is latency-bound at the particle counts of interest (one exp per particle), so it spreads a
-// tile over APS_K2_THREADS = 512 threads (4 particles each) instead of the 128 of the resampler.
-#define APS_K2_THREADS 512
+// tile over APS_K2_THREADS = 256 threads (8 particles each) instead of the 128 of the resampler;
+// all 489 tiles of N = 1e6 are then resident at once (4 blocks per SM).
+#ifndef APS_K2_THREADS
+#define APS_K2_THREADS 256   // measured standalone at N = 1e6: 256 threads 15.9 us, 512 threads 16.7 us
+#endif
 #define APS_K2_IPT (APS_TILE / APS_K2_THREADS)
 #define APS_K2_WARPS (APS_K2_THREADS / 32)
 template <int INPUT>
 __global__ void __launch_bounds__(APS_K2_THREADS) k_normalise(const __grid_constant__ DevCtx c, const double *__restrict__ in,
                                                            const long long s) {
     __shared__ u64 red[APS_K2_WARPS];
+    __shared__ u64 s_tot[3];
     __shared__ unsigned s_last;
     const long long N = c.N;
     const long long base = (long long)blockIdx.x * APS_TILE;
     StepAcc *acc = &c.acc[s];
+    if (threadIdx.x < 3) s_tot[threadIdx.x] = 0;
+    __syncthreads();
     u64 max_enc = acc->max_enc;
     unsigned bad_in = 0;
     const bool multi = c.world > 1;
@@ -370,13 +376,21 @@ __global__ void __launch_bounds__(APS_K2_THREADS) k_normalise(const __grid_const
             s2 += qs * qs;
         }
     }
-    s0 = block_sum_u64<APS_K2_WARPS>(s0, red);
-    s1 = block_sum_u64<APS_K2_WARPS>(s1, red);
-    s2 = block_sum_u64<APS_K2_WARPS>(s2, red);
+    // tile totals: warp shuffles, then one shared-memory integer atomic per warp and total
+    // (exact integers, so the order is irrelevant; cheaper than three block-wide reductions)
+    s0 = warp_sum_u64(s0);
+    s1 = warp_sum_u64(s1);
+    s2 = warp_sum_u64(s2);
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(&s_tot[0], s0);
+        atomicAdd(&s_tot[1], s1);
+        atomicAdd(&s_tot[2], s2);
+    }
+    __syncthreads();
     if (threadIdx.x == 0) {
-        c.tile_sum[blockIdx.x] = s0;
-        c.tile_s1[blockIdx.x] = s1;
-        c.tile_s2[blockIdx.x] = s2;
+        c.tile_sum[blockIdx.x] = s_tot[0];
+        c.tile_s1[blockIdx.x] = s_tot[1];
+        c.tile_s2[blockIdx.x] = s_tot[2];
         __threadfence();
         const unsigned ticket = atomicAdd(&acc->done_ctr, 1u);
         s_last = (ticket == gridDim.x - 1) ? 1u : 0u;
@@ -1562,6 +1576,57 @@ __global__ void __launch_bounds__(APS_THREADS) k_gather_final(const __grid_const
          i += (long long)gridDim.x * APS_THREADS) {
         const long long a = anc[i];
         for (int k = 0; k < D; ++k) out[i * D + k] = load_state(c, (T - 1) % c.x_slabs, k, a);
+    }
+}
+
+// ---------------------------------------------------------------- smoothing summaries over the genealogy
+// One backward step of the weighted trajectory mean E[x_t | y_1:T] ~ sum_i W_i x_t[b_t(i)], where
+// b_t(i) is the time-t ancestor of final particle i (b_T = anc_{T+1}, b_{t-1} = anc_t[b_t]).
+// idx holds b_t(i) for this rank's slots on entry and b_{t-1}(i) on exit. Block partial sums are
+// combined by the last block in block order, so the result does not depend on scheduling.
+#define APS_SMOOTH_BLOCKS 296
+__global__ void __launch_bounds__(APS_K1_THREADS) k_smooth_step(const __grid_constant__ DevCtx c, const long long t,
+                                                             int32_t *__restrict__ idx, const u64 *__restrict__ q,
+                                                             const int uniform, double *__restrict__ partial,
+                                                             unsigned *done_ctr, double *__restrict__ mean_out) {
+    __shared__ double red[APS_K1_THREADS / 32][APS_MAX_D];
+    __shared__ unsigned s_last;
+    const long long N = c.N, T = c.T;
+    const int D = c.d;
+    const StepPlan &p = c.plan[T];
+    const double Qd = uniform ? (double)c.Ng : (double)p.Q;
+    double acc[APS_MAX_D] = {0.0, 0.0, 0.0, 0.0};
+    for (long long i = (long long)blockIdx.x * APS_K1_THREADS + threadIdx.x; i < N;
+         i += (long long)gridDim.x * APS_K1_THREADS) {
+        const long long b = t == T ? (long long)c.anc[(T % c.anc_slabs) * c.NS + i] : (long long)idx[i];
+        const double w = (uniform ? 1.0 : (double)q[i]) / Qd;
+        for (int k = 0; k < D; ++k) acc[k] += w * load_state(c, (t - 1) % c.x_slabs, k, b);
+        idx[i] = t > 1 ? (int32_t)load_anc(c, (t - 1) % c.anc_slabs, b) : 0;
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int k = 0; k < APS_MAX_D; ++k) {
+        double v = acc[k];
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+        if (lane == 0) red[warp][k] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < APS_MAX_D) {
+        double v = 0.0;
+        for (int w = 0; w < APS_K1_THREADS / 32; ++w) v += red[w][threadIdx.x];
+        partial[(long long)blockIdx.x * APS_MAX_D + threadIdx.x] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        s_last = atomicAdd(done_ctr + (t - 1), 1u) == gridDim.x - 1 ? 1u : 0u;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    if (threadIdx.x < D) {
+        double v = 0.0;
+        for (unsigned b = 0; b < gridDim.x; ++b) v += __ldcg(&partial[(long long)b * APS_MAX_D + threadIdx.x]);
+        mean_out[(t - 1) * D + threadIdx.x] = v;
     }
 }
 

@@ -155,6 +155,10 @@ class SMCSample:
         self.logevidence = logevidence
         self.trajectories = _LazyTrajectories(handle, tssm)
 
+    def smoothed_mean(self):
+        """Weighted mean trajectory sum_i W_i X_i (T x d), computed on the device from the genealogy."""
+        return self._h.smoothing_mean()
+
 
 class _LazyTrajectories:
     def __init__(self, handle, tssm):

@@ -108,6 +108,12 @@ int aps_get_step_stats(aps_handle *h, double *logz_out /* T */, double *ess_out 
  * build time t (2..T+1; T+1 = final resampled set) as N int32, 0-based.                         */
 int aps_get_states(aps_handle *h, int64_t t, double *x_out);
 int aps_get_ancestors(aps_handle *h, int64_t t, int32_t *anc_out);
+/* Smoothing summary without materialising trajectories on the host: mean_out[t][k] =
+ * sum_i W_i X_i[t][k] over the final weighted particle set, X_i = trajectory of final particle i
+ * (what examples/gaussian-ssm/script.jl:89-101 computes from collect(pc) on the host). One
+ * backward pass over the ancestor store, O(N T) on the device, T x d doubles back. Sharded
+ * handles return this rank's partial sums (add the ranks' results on the host).               */
+int aps_smoothing_mean(aps_handle *h, double *mean_out /* T x d */);
 /* diagnostics: number of "fat" parents (children deferred to the consumer kernel)
  * recorded on this rank at each decision point s = 0..T of the last sweep                        */
 int aps_get_fat_counts(aps_handle *h, int32_t *counts_out /* T+1 */);

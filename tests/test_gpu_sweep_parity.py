@@ -177,3 +177,23 @@ def test_not_normalisable_weights_raise():
     with pytest.raises(_lib.ApsError) as e:
         h.sweep(1)
     assert e.value.code == _abi.ERR_WEIGHTS
+
+
+@pytest.mark.parametrize("thr", [float("nan"), 0.5])
+def test_smoothing_mean_matches_host_backtrace(thr):
+    """N2: weighted mean trajectory from the device genealogy == the same sum formed on
+    the host from the oracle's state / ancestor history (fp64 sums in a different order: 1e-12)."""
+    m = models.lg4()
+    N, T = 6000, 9
+    cfg, Y, ro, h, le = run_both(m, N, T, 4, 0xDA7A0003, ess_threshold=thr)
+    b = ro.anc_hist[T].astype(np.int64)
+    want = np.zeros((T, m.d))
+    for t in range(T, 0, -1):
+        want[t - 1] = (ro.final_w[:, None] * ro.x_hist[t - 1][b]).sum(axis=0)
+        b = ro.anc_hist[t - 1][b].astype(np.int64)
+    got = h.smoothing_mean()
+    assert np.allclose(got, want, rtol=1e-12, atol=1e-13)
+    # and it is what averaging the materialised trajectories gives
+    some = [0, 1, N // 2, N - 1]
+    for i in some:
+        assert np.array_equal(h.trajectory(i), O.trajectory(cfg, i, ro))
