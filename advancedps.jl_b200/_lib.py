@@ -20,7 +20,7 @@ _HDR = [os.path.join(_HERE, "..", "include", f) for f in ("aps_b200.h", "aps_mod
 EXPORTS = [
     "aps_create", "aps_destroy", "aps_set_observations", "aps_sweep", "aps_sweep_profiled",
     "aps_pick_trajectory",
-    "aps_get_weights", "aps_get_logweights", "aps_get_final_states", "aps_get_trajectory",
+    "aps_get_weights", "aps_get_weights_view", "aps_get_logweights", "aps_get_final_states", "aps_get_trajectory",
     "aps_get_step_stats", "aps_get_states", "aps_get_ancestors", "aps_get_fat_counts", "aps_smoothing_mean", "aps_last_sweep_ms",
     "aps_last_sweep_launches", "aps_resample", "aps_logsumexp", "aps_softmax", "aps_ess",
     "aps_randcat", "aps_bench_resample", "aps_ipc_export", "aps_ipc_import", "aps_last_error",
@@ -147,6 +147,15 @@ class Handle:
     def weights(self):
         w = np.zeros(self.N)
         check(lib().aps_get_weights(self._h, ptr(w)))
+        return w
+
+    def weights_view(self):
+        """Normalised weights as a read-only numpy view of the handle's pinned host buffer (no staging
+        copy); valid until the next call on this handle."""
+        p = C.POINTER(C.c_double)()
+        check(lib().aps_get_weights_view(self._h, C.byref(p)))
+        w = np.ctypeslib.as_array(p, shape=(self.N,))
+        w.flags.writeable = False
         return w
 
     def logweights(self):

@@ -206,6 +206,7 @@ struct aps_handle {
     int *d_counts, *d_tile_count, *d_tile_cprefix;
     ResidualState *d_rs;   // one per decision point
     unsigned *d_done2;     // one per decision point
+    double *h_weights;                          // pinned staging of aps_get_weights_view (lazily allocated)
     SweepParams *h_sp;                          // pinned
     SweepState *h_st;                           // pinned
     cudaGraphExec_t graph;
@@ -255,6 +256,7 @@ static void free_handle(aps_handle *h) {
     for (int i = 0; i < h->n_ipc_opened; ++i) cudaIpcCloseMemHandle(h->ipc_opened[i]);
     cudaFree(h->d_mail);
     cudaFree(h->d_peers);
+    if (h->h_weights) cudaFreeHost(h->h_weights);
     if (h->h_sp) cudaFreeHost(h->h_sp);
     if (h->h_st) cudaFreeHost(h->h_st);
     if (h->ev0) cudaEventDestroy(h->ev0);
@@ -649,6 +651,19 @@ extern "C" int aps_get_weights(aps_handle *h, double *w_out) {
     CU(cudaMemcpyAsync(w_out, h->d_scratch, sizeof(double) * (size_t)c.N, cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     CU(cudaGetLastError());
+    return APS_OK;
+}
+
+extern "C" int aps_get_weights_view(aps_handle *h, const double **w_out) {
+    NEED_SWEEP("aps_get_weights_view");
+    if (!w_out) return fail(APS_ERR_INVALID, "aps_get_weights_view: null output");
+    const DevCtx &c = h->ctx;
+    if (!h->h_weights) CU(cudaMallocHost(&h->h_weights, sizeof(double) * (size_t)c.N));  // pinned, owned by the handle
+    k_weights_out<<<stride_grid(c.N), APS_THREADS, 0, h->stream>>>(c.q, c.plan + c.T, c.N, c.Ng, c.S, 1, h->d_scratch);
+    CU(cudaMemcpyAsync(h->h_weights, h->d_scratch, sizeof(double) * (size_t)c.N, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaGetLastError());
+    *w_out = h->h_weights;
     return APS_OK;
 }
 

@@ -222,7 +222,9 @@ def sample(rng, model, sampler, n_iter=None, **kwargs):
             warnings.warn(f"keyword arguments {tuple(kwargs)} are not supported by `SMC`")  # smc.jl:41-43
         h = _handle_for(model, sampler)
         logev = h.sweep(_draw_key(rng))
-        return SMCSample(h, model, h.weights(), logev)
+        # weights: a view of the handle's pinned host buffer (valid until the next call on this
+        # model's handle; copy it to keep it) -- the D2H copy runs at DMA speed, no staging pass
+        return SMCSample(h, model, h.weights_view(), logev)
     if n_iter is None:
         raise TypeError("sample(rng, model, PG|PGAS, n_iter): n_iter is required")
     out, state = [], None

@@ -267,7 +267,7 @@ def main():
         def e2e_step():  # same calls sample() makes, on this rank's shard
             h.set_observations(Y)
             h.sweep(int(rng.integers(0, 2**63)))
-            return h.weights()
+            return h.weights_view()
     for _ in range(args.warmup):
         e2e_step()
     barrier()

@@ -99,6 +99,9 @@ int aps_pick_trajectory(aps_handle *h, double *traj_out, int64_t *index_out);
 
 /* SMCSample fields (src/smc.jl:23-27,56) materialised lazily.                                  */
 int aps_get_weights(aps_handle *h, double *w_out /* N */);                 /* getweights, container.jl:95 */
+/* same weights without a staging copy: *w_out points to a pinned host buffer owned by the handle
+ * (N doubles), valid until the next call on this handle (Julia: unsafe_wrap; numpy: a view)       */
+int aps_get_weights_view(aps_handle *h, const double **w_out);
 int aps_get_logweights(aps_handle *h, double *logw_out /* N */);           /* pc.logWs                    */
 int aps_get_final_states(aps_handle *h, double *x_out /* N x d */);        /* collect(pc), last state     */
 int aps_get_trajectory(aps_handle *h, int64_t slot, double *traj_out /* T x d */);

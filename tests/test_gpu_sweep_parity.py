@@ -150,6 +150,12 @@ def test_conditional_sweeps(sampler):
     assert h.sweep(77, ref_on_device=True) == ro.logevidence
 
 
+def test_weights_view_is_the_weights():
+    cfg, Y, ro, h, le = run_both(models.linear_gaussian(), 5000, 9, 3, 2, ess_threshold=0.0)
+    v = h.weights_view()
+    assert not v.flags.writeable and np.array_equal(v, ro.final_w) and np.array_equal(h.weights(), v)
+
+
 def test_final_states():
     m = models.linear_gaussian()
     cfg, Y, ro, h, le = run_both(m, 5000, 9, 3, 2, ess_threshold=0.5)
