@@ -299,8 +299,13 @@ def main():
             gbs = alg_bytes[nm] * N_PARTICLES / (avg * 1e-3) / 1e9 if nm in alg_bytes else None
             kern[nm] = {"launches": n, "avg_us": 1e3 * avg, "share": ms / tot_ms, "alg_GBps": gbs}
     dom = max((k for k in kern if k in alg_bytes), key=lambda k: kern[k]["share"])
+    try:  # dram bytes per launch from the committed ncu --set full captures (profiles/)
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic_r01.json")) as f:
+            ncu_traffic = json.load(f)
+    except (OSError, ValueError):
+        ncu_traffic = {}
     roofline = {"bound": "hbm", "kernel": dom, "achieved": kern[dom]["alg_GBps"], "peak": peak, "unit": "GB/s",
-                "frac": kern[dom]["alg_GBps"] / peak, "traffic": None, "peak_source": peak_src,
+                "frac": kern[dom]["alg_GBps"] / peak, "traffic": ncu_traffic.get(dom), "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes[dom] * N_PARTICLES,
                 "note": "N=1e6 per launch is L2-resident and latency-bound; see resample_isolated for the streaming figure",
                 "kernels": kern}
@@ -311,6 +316,7 @@ def main():
         iso = 12 * n_iso / (avg_ms * 1e-3) / 1e9
         roofline["resample_isolated"] = {"n": n_iso, "avg_ms": avg_ms, "min_ms": min_ms, "achieved": iso,
                                          "frac": iso / peak, "algorithmic_bytes_per_launch": 12 * n_iso,
+                                         "traffic": ncu_traffic.get("k_resample_isolated_n2^25"),
                                          "l2": "flushed between launches (512 MB memset, then a 256 MB streaming read so L2 is cold and clean)"}
     barrier()
 
