@@ -203,6 +203,8 @@ struct aps_handle {
     double *d_ref, *d_traj, *d_Y, *d_scratch;  // d_scratch: N x d doubles for accessors
     // multinomial / residual resampling scratch
     u64 *d_cum, *d_rq;
+    unsigned short *d_cut;
+    unsigned char *d_cut_sh;
     int *d_counts, *d_tile_count, *d_tile_cprefix;
     ResidualState *d_rs;   // one per decision point
     unsigned *d_done2;     // one per decision point
@@ -247,6 +249,8 @@ static void free_handle(aps_handle *h) {
     cudaFree(h->d_Y);
     cudaFree(h->d_scratch);
     cudaFree(h->d_cum);
+    cudaFree(h->d_cut);
+    cudaFree(h->d_cut_sh);
     cudaFree(h->d_rq);
     cudaFree(h->d_counts);
     cudaFree(h->d_tile_count);
@@ -354,6 +358,8 @@ extern "C" int aps_create(const aps_config *cfg, aps_handle **out) {
     if (world > 1) CUH(cudaMalloc(&h->d_peers, sizeof(PeerTable)));
     if (cfg->resampler == APS_RESAMPLE_MULTINOMIAL || cfg->resampler == APS_RESAMPLE_RESIDUAL) {
         CUH(cudaMalloc(&h->d_cum, sizeof(u64) * (size_t)c.NS));
+        CUH(cudaMalloc(&h->d_cut, sizeof(unsigned short) * (size_t)c.num_tiles * APS_CUT));
+        CUH(cudaMalloc(&h->d_cut_sh, (size_t)c.num_tiles));
         CUH(cudaMalloc(&h->d_counts, sizeof(int) * (size_t)c.NS));
         CUH(cudaMalloc(&h->d_tile_count, sizeof(int) * (size_t)c.num_tiles));
         CUH(cudaMalloc(&h->d_tile_cprefix, sizeof(int) * (size_t)c.num_tiles));
@@ -460,6 +466,8 @@ static long long enqueue_sweep(aps_handle *h, LaunchProf *prof = nullptr) {
             MultiArgs a;
             memset(&a, 0, sizeof(a));
             a.cum = h->d_cum;
+            a.cut = h->d_cut;
+            a.cut_sh = h->d_cut_sh;
             a.counts = h->d_counts;
             a.tile_count = h->d_tile_count;
             a.tile_cprefix = h->d_tile_cprefix;
@@ -482,7 +490,6 @@ static long long enqueue_sweep(aps_handle *h, LaunchProf *prof = nullptr) {
                     a.range_len = &c.acc[t].tot[0];
                 }
                 cudaMemsetAsync(h->d_counts, 0, sizeof(int) * (size_t)c.N, st);
-                cudaMemsetAsync(h->d_tile_count, 0, sizeof(int) * (size_t)c.num_tiles, st);
             } else {
                 a.qsrc = h->d_rq;
                 a.wplan = c.plan + c.T + 1;
@@ -501,6 +508,7 @@ static long long enqueue_sweep(aps_handle *h, LaunchProf *prof = nullptr) {
             // sharded: every rank makes all Ng draws and keeps those in its own weight range
             const int gs = stride_grid((c.Ng + 1) / 2);
             APS_LAUNCH(2, k_multi_search<1><<<gs, APS_K1_THREADS, 0, st>>>(a, &h->d_sp->key));
+            APS_LAUNCH(2, k_tile_counts<<<gt, APS_THREADS, 0, st>>>(a));
             APS_LAUNCH(2, k_scan_tile_counts<<<1, APS_THREADS, 0, st>>>(a, nullptr, c, t));
             APS_LAUNCH(2, k_expand_counts<<<gt, APS_THREADS, 0, st>>>(a, anc_slab(t), 1, c, t));
         }
@@ -808,6 +816,8 @@ struct OpWorkspace {
     int32_t *d_idx32 = nullptr;
     long long *d_idx64 = nullptr;
     u64 *d_cum = nullptr, *d_rq = nullptr;
+    unsigned short *d_cut = nullptr;
+    unsigned char *d_cut_sh = nullptr;
     int *d_counts = nullptr, *d_tile_count = nullptr, *d_tile_cprefix = nullptr;
     ResidualState *d_rs = nullptr;
     unsigned *d_done2 = nullptr;
@@ -838,7 +848,7 @@ static int ws_reserve(OpWorkspace &w, long long m, long long n) {
     if (m > w.cap_m) {
         cudaFree(w.d_in); cudaFree(w.d_wout); cudaFree(w.d_q);
         cudaFree(w.tile_sum); cudaFree(w.tile_s1); cudaFree(w.tile_s2); cudaFree(w.tile_prefix);
-        cudaFree(w.d_cum); cudaFree(w.d_rq); cudaFree(w.d_counts); cudaFree(w.d_tile_count); cudaFree(w.d_tile_cprefix);
+        cudaFree(w.d_cum); cudaFree(w.d_rq); cudaFree(w.d_cut); cudaFree(w.d_cut_sh); cudaFree(w.d_counts); cudaFree(w.d_tile_count); cudaFree(w.d_tile_cprefix);
         w.cap_m = 0;
         const long long nt = (m + APS_TILE - 1) / APS_TILE;
         CU(cudaMalloc(&w.d_in, sizeof(double) * (size_t)m));
@@ -849,6 +859,8 @@ static int ws_reserve(OpWorkspace &w, long long m, long long n) {
         CU(cudaMalloc(&w.tile_s2, sizeof(u64) * (size_t)nt));
         CU(cudaMalloc(&w.tile_prefix, sizeof(u64) * (size_t)nt));
         CU(cudaMalloc(&w.d_cum, sizeof(u64) * (size_t)(m + 32)));
+        CU(cudaMalloc(&w.d_cut, sizeof(unsigned short) * (size_t)nt * APS_CUT));
+        CU(cudaMalloc(&w.d_cut_sh, (size_t)nt));
         CU(cudaMalloc(&w.d_rq, sizeof(u64) * (size_t)(m + 32)));
         CU(cudaMalloc(&w.d_counts, sizeof(int) * (size_t)(m + 32)));
         CU(cudaMalloc(&w.d_tile_count, sizeof(int) * (size_t)nt));
@@ -965,6 +977,8 @@ extern "C" int aps_resample(int kind, const double *wts, int64_t m, int64_t n, u
         MultiArgs a;
         memset(&a, 0, sizeof(a));
         a.cum = w.d_cum;
+        a.cut = w.d_cut;
+        a.cut_sh = w.d_cut_sh;
         a.counts = w.d_counts;
         a.tile_count = w.d_tile_count;
         a.tile_cprefix = w.d_tile_cprefix;
@@ -987,6 +1001,7 @@ extern "C" int aps_resample(int kind, const double *wts, int64_t m, int64_t n, u
             a.n_draws = &w.d_rs->n_rest;
             a.out_offset = &w.d_rs->n_det;
             k_residual_split<<<gt, APS_THREADS, 0, w.stream>>>(a, w.d_q, w.d_rq, w.d_rs);
+            k_tile_counts<<<gt, APS_THREADS, 0, w.stream>>>(a);
             k_scan_tile_counts<<<1, APS_THREADS, 0, w.stream>>>(a, nullptr, c, 0);
             k_expand_counts<<<gt, APS_THREADS, 0, w.stream>>>(a, w.d_idx32, 0, c, 0);
             k_fill_fat<<<sm_count() * 2, APS_K1_THREADS, 0, w.stream>>>(c, 0, w.d_idx32, 0);

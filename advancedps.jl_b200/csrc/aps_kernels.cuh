@@ -984,9 +984,21 @@ struct MultiArgs {
     // into its own weight range [*range_lo, *range_lo + *range_len)
     const u64 *range_lo, *range_len;
     long long *child_off;   // out: children owned by parents of lower ranks (k_scan_tile_counts)
+    // cut-point (guide) table of the inverse CDF, built by k_cumsum: entry b of a tile is the first
+    // tile-local element whose cumulative weight exceeds b << cut_sh[tile] (tile-relative units)
+    unsigned short *cut;    // [num_tiles][APS_CUT]
+    unsigned char *cut_sh;  // [num_tiles]
 };
+#define APS_CUT_BITS 10
+#define APS_CUT ((1 << APS_CUT_BITS) + 1)   // entries per tile: <= 1024 buckets + one sentinel
 
-// inclusive cumulative sums of one tile of qsrc (thread-blocked, 16 per thread)
+// inclusive cumulative sums of one tile of qsrc (thread-blocked, 16 per thread) and the tile's
+// cut-point table: the tile's weight range [0, S) is cut into <= 1024 equal buckets of 2^sh units;
+// element j covers the tile-relative interval [C_{j-1}, C_j) and is the answer ("first element
+// whose cumulative weight exceeds v") for every bucket boundary v = b << sh inside it. A draw then
+// needs one table read and a binary search inside a bracket of a few elements instead of 11 steps
+// over the whole tile (measured first: a forward scan from the cut point -- the longest scan of a
+// warp's 32 lanes was ~70 elements with 256 buckets, no faster than the plain binary search).
 __global__ void __launch_bounds__(APS_THREADS) k_cumsum(const __grid_constant__ MultiArgs a) {
     __shared__ u64 red[APS_WARPS];
     if (!a.plan->resampled || a.plan->err) return;
@@ -997,10 +1009,30 @@ __global__ void __launch_bounds__(APS_THREADS) k_cumsum(const __grid_constant__ 
 #pragma unroll
     for (int r = 1; r < APS_IPT; ++r) cum[r] += cum[r - 1];
     u64 tot;
-    const u64 excl = block_excl_scan_u64<APS_WARPS>(cum[APS_IPT - 1], red, &tot) + a.tile_prefix[blockIdx.x];
+    const u64 excl_rel = block_excl_scan_u64<APS_WARPS>(cum[APS_IPT - 1], red, &tot);
+    const u64 excl = excl_rel + a.tile_prefix[blockIdx.x];
 #pragma unroll
     for (int r = 0; r < APS_IPT; ++r)
         if (base + r < a.N) a.cum[base + r] = excl + cum[r];
+    // cut points
+    const int bits = tot ? 64 - __clzll((long long)tot) : 0;
+    const int sh = bits > APS_CUT_BITS ? bits - APS_CUT_BITS : 0;
+    if (threadIdx.x == 0) a.cut_sh[blockIdx.x] = (unsigned char)sh;
+    unsigned short *cut = a.cut + (long long)blockIdx.x * APS_CUT;
+    if (threadIdx.x == 0) {  // sentinel behind the last used bucket: upper bracket of draws in that bucket
+        const long long last = (base + APS_TILE < a.N ? (long long)APS_TILE : a.N - base) - 1;
+        cut[tot ? ((tot - 1) >> sh) + 1 : 0] = (unsigned short)(last > 0 ? last : 0);
+    }
+    u64 prev = excl_rel;
+#pragma unroll 1
+    for (int r = 0; r < APS_IPT; ++r) {
+        const u64 cur = excl_rel + cum[r];
+        if (cur > prev) {
+            const u64 b0 = (prev + ((1ull << sh) - 1)) >> sh, b1 = (cur - 1) >> sh;  // buckets with prev <= b << sh < cur
+            for (u64 b = b0; b <= b1; ++b) cut[b] = (unsigned short)(threadIdx.x * APS_IPT + r);
+        }
+        prev = cur;
+    }
 }
 
 // i.i.d. draws: draw i is word (i & 1) of Philox block i >> 1, so one thread makes two draws; each
@@ -1032,25 +1064,41 @@ __global__ void __launch_bounds__(APS_K1_THREADS) k_multi_search(const __grid_co
                 else hi = mid - 1;
             }
             const long long tile = lo;
-            long long jl = tile * APS_TILE, jh = jl + APS_TILE < a.N ? jl + APS_TILE : a.N;
-            --jh;  // first j in [jl, jh] with cum[j] > tau (exists unless trailing zero weights)
+            // first j of the tile with cum[j] > tau: the cut points of tau's bucket and of the next
+            // one bracket it (usually a handful of elements), binary search inside the bracket
+            const u64 trel = tau - a.tile_prefix[tile];
+            const unsigned short *cp = a.cut + tile * APS_CUT + (long long)(trel >> a.cut_sh[tile]);
+            long long jl = tile * APS_TILE + cp[0], jh = tile * APS_TILE + cp[1];
             while (jl < jh) {
                 const long long mid = (jl + jh) >> 1;
                 if (a.cum[mid] > tau) jh = mid;
                 else jl = mid + 1;
             }
             if (TO_COUNTS) {
-                // warp-aggregated histogram: lanes that drew the same parent issue one atomic
-                const unsigned act = __activemask();
-                const unsigned same = __match_any_sync(act, (int)jl);
-                if ((int)(__ffs(same) - 1) == (int)(threadIdx.x & 31)) atomicAdd(&a.counts[jl], __popc(same));
-                const unsigned samet = __match_any_sync(act, (int)tile);
-                if ((int)(__ffs(samet) - 1) == (int)(threadIdx.x & 31)) atomicAdd(&a.tile_count[tile], __popc(samet));
+                // integer histogram of the offspring counts. (Per-tile totals are NOT accumulated here:
+                // the 489 tile counters share 16 cache lines, and 10^6 atomics on them serialised in
+                // L2 -- 150 us of this kernel's 170 us; k_tile_counts sums them afterwards.)
+                atomicAdd(&a.counts[jl], 1);
             } else {
                 a.out32[off + i] = (int32_t)jl;
             }
         }
     }
+}
+
+// per-tile totals of the offspring counts (one tile per block, coalesced)
+__global__ void __launch_bounds__(APS_THREADS) k_tile_counts(const __grid_constant__ MultiArgs a) {
+    __shared__ u64 red[APS_WARPS];
+    if (!a.plan->resampled || a.plan->err) return;
+    const long long base = (long long)blockIdx.x * APS_TILE;
+    u64 sum = 0;
+#pragma unroll
+    for (int r = 0; r < APS_IPT; ++r) {
+        const long long j = base + r * APS_THREADS + threadIdx.x;
+        if (j < a.N) sum += (u64)a.counts[j];
+    }
+    sum = block_sum_u64<APS_WARPS>(sum, red);
+    if (threadIdx.x == 0) a.tile_count[blockIdx.x] = (int)sum;
 }
 
 // exclusive scan of the per-tile offspring counts (one block). Sharded: the ranks exchange their
