@@ -95,3 +95,67 @@ def test_shard_bounds_and_totals():
         D.shard_bounds(1000, 8, 0)
     assert D.combine_totals([5, 7, 11], 2) == (23, 12)
     assert D.combine_totals([2**61, 2**61], 0) == (2**62, 0)
+
+
+def _worker_multinomial(rank, world, port, n_global, tmpdir):
+    """Sharded multinomial step as the kernels do it: every rank makes ALL draws (two per Philox
+    block), keeps those whose integer threshold falls into its own weight range, histograms them
+    over its own parents; offspring totals are exchanged so that children are laid out grouped by
+    parent in global parent order. Must equal the unsharded oracle's draw list."""
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import ctypes as Ct
+
+    import oracle as O
+    from advancedps_b200 import distributed as D
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        rng = np.random.default_rng(321)
+        logw_all = -0.5 * (2.0 * rng.normal(size=n_global)) ** 2
+        lo, hi = D.shard_bounds(n_global, world, rank)
+        m = torch.tensor([logw_all[lo:hi].max()], dtype=torch.float64)
+        dist.all_reduce(m, op=dist.ReduceOp.MAX)
+        q, Qr = O.quantise_shard(logw_all[lo:hi], float(m.item()), n_global)
+        tot = [None] * world
+        dist.all_gather_object(tot, int(Qr))
+        Q, offset = D.combine_totals(tot, rank)
+        cum = np.cumsum(q.astype(object))                      # exact python ints, local inclusive sums
+        key, step, n = 99, 4, n_global
+        counts = np.zeros(hi - lo, dtype=np.int64)
+        for p in range((n + 1) // 2):                          # every rank makes all draws
+            w = O.philox2x64(p, (step << 16) | (1 << 8), key)
+            for h in range(2):
+                i = 2 * p + h
+                if i >= n:
+                    continue
+                tau = ((w[h] >> 11) * Q) >> 53
+                if offset <= tau < offset + int(Qr):           # ... and keeps those in its own range
+                    counts[int(np.searchsorted(cum, tau - offset, side="right"))] += 1
+        ctot = [None] * world
+        dist.all_gather_object(ctot, int(counts.sum()))
+        assert sum(ctot) == n
+        child_off = sum(ctot[:rank])                           # children of lower ranks' parents come first
+        mine = np.repeat(np.arange(lo, hi), counts)            # global parent ids of children child_off..
+        allc = [None] * world
+        dist.all_gather_object(allc, (child_off, mine))
+        anc = np.full(n, -1, dtype=np.int64)
+        for off, par in allc:
+            anc[off:off + len(par)] = par
+        # unsharded oracle: draw list -> counts -> grouped by parent (src/container.jl:185-217)
+        qa, _, Qa = O.quantise_logw(logw_all)
+        idx = np.zeros(n, dtype=np.int64)
+        O._chk(O.lib().orc_resample_multinomial_canon(O._ptr(qa), Ct.c_int64(n), Ct.c_int64(n), Ct.c_uint64(key),
+                                                      Ct.c_uint64(step), O._ptr(idx)))
+        want = np.repeat(np.arange(n), np.bincount(idx - 1, minlength=n))
+        np.save(os.path.join(tmpdir, f"okm_{rank}.npy"), np.array([int(Qa == Q and np.array_equal(anc, want))]))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_sharded_multinomial_matches_unsharded(tmp_path):
+    port = 29900 + (os.getpid() % 90)
+    mp.spawn(_worker_multinomial, args=(2, port, 2048, str(tmp_path)), nprocs=2, join=True)
+    assert all(int(np.load(tmp_path / f"okm_{r}.npy")[0]) == 1 for r in range(2))
