@@ -96,12 +96,8 @@ __global__ void __launch_bounds__(APS_K1_THREADS) k_propagate(const __grid_const
                                                            double *__restrict__ xt, const double *__restrict__ xp,
                                                            const int32_t *anc) {  // not __restrict__: patched below
     __shared__ u64 red[APS_K1_THREADS / 32];
-    SpanProbe probe(&c.acc[t], 0, c.dbg & 16);
     const long long N = c.N, NS = c.NS;
-    // log-weights start at zero in every sweep (src/smc.jl:45-51); afterwards they restart from
-    // zero only when the previous decision point resampled (reset_logweights!, container.jl:228)
-    const bool reset = t == 1 || c.plan[t - 1].resampled != 0;
-    const int has_ref = c.sp->has_ref;
+    const int has_ref = c.sp->has_ref;   // (sweep parameters: written before the graph is launched)
     const u64 key = c.sp->key;
     const double *__restrict__ y = c.Y + (t - 1) * c.dy;
 
@@ -135,10 +131,15 @@ __global__ void __launch_bounds__(APS_K1_THREADS) k_propagate(const __grid_const
             }
         }
     };
-    if (!MULTI) resolve_fat();
-    // the normals do not depend on the ancestors: draw the first pair's before waiting for the peers
+    // the normals do not depend on the ancestors (nor, sharded, on the peers): draw the first pair's
+    // before the loads / the wait for the peers
     double z[2 * D];
     if (p < npairs) aps_pair_normals<D>(key, (u64)(pair0 + p), (u64)t, z);
+    if (!MULTI) resolve_fat();
+    SpanProbe probe(&c.acc[t], 0, c.dbg & 16);
+    // log-weights start at zero in every sweep (src/smc.jl:45-51); afterwards they restart from
+    // zero only when the previous decision point resampled (reset_logweights!, container.jl:228)
+    const bool reset = t == 1 || c.plan[t - 1].resampled != 0;
     if (MULTI) {
         // the ancestor scatter of step t-1 (peer stores from every rank) must have landed: this
         // rank's resample kernel is complete (stream order), so block 0 tells every rank, and
