@@ -155,3 +155,48 @@ def test_sharded_conditional_sweeps(sampler, world, res):
     tr = collective(hs, lambda h: h.trajectory(nl - 1))
     for r, t_r in enumerate(tr):
         assert np.array_equal(t_r, O.trajectory(cfg, (r + 1) * nl - 1, ro))
+
+
+@pytest.mark.parametrize("world,N,T", [(2, 64, 1), (2, 64, 2), (4, 128, 3), (8, 256, 2)])
+def test_sharded_minimal_sizes(world, N, T):
+    """Smallest legal shards (32 slots per rank), one- and two-step sweeps."""
+    m = models.linear_gaussian()
+    _, Y = O.simulate_data(m, T, 1)
+    hs, out = run_sharded(m, N, T, Y, [8], world)
+    ro = O.sweep(_abi.make_config(m, N, T), Y, 8, mode=O.CANON)
+    assert_sharded_equal(hs, out[0], ro, N, T)
+
+
+def test_sharded_without_history_even_and_odd_steps():
+    """keep_history = 0 keeps two state / ancestor slabs: peers read slab (t-1) % 2 while a fast rank
+    may already be in the next sweep -- the exchange at the start of k_propagate(t = 1) orders them."""
+    m = models.linear_gaussian()
+    for T in (6, 7):
+        _, Y = O.simulate_data(m, T, 2)
+        hs = []
+        for r in range(2):
+            cfg = _abi.make_config(m, 8192, T, keep_history=False, rank=r, world_size=2)
+            h = _lib.Handle(cfg)
+            h.set_observations(Y)
+            hs.append(h)
+        blobs = [h.ipc_export() for h in hs]
+        [h.ipc_import(blobs) for h in hs]
+        for seed in (1, 2, 3, 4):
+            les = collective(hs, lambda h: h.sweep(seed))
+            ro = O.sweep(_abi.make_config(m, 8192, T), Y, seed, mode=O.CANON)
+            assert all(le == ro.logevidence for le in les)
+            assert np.array_equal(np.concatenate([h.weights() for h in hs]), ro.final_w)
+
+
+def test_sharded_not_normalisable_raises_on_every_rank():
+    m = models.constant_loglik()
+    hs = make_ranks(m, 4096, 2, np.full((2, 1), -np.inf), 2)
+
+    def run(h):
+        try:
+            h.sweep(1)
+            return None
+        except _lib.ApsError as e:
+            return e.code
+
+    assert collective(hs, run) == [_abi.ERR_WEIGHTS, _abi.ERR_WEIGHTS]
