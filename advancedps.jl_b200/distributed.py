@@ -47,3 +47,76 @@ def create_sharded_handle(model, n_global, n_steps, Y, resampler=_abi.RESAMPLE_S
     h.ipc_import([np.frombuffer(b, dtype=np.uint8) for b in blobs])
     dist.barrier(group=group)
     return h
+
+
+# ------------------------------------------------------------------ sampler surface, sharded
+_sharded = {}
+
+
+def _shared_key(rng, group=None):
+    """One rand(rng, UInt64) drawn on rank 0 and broadcast: every rank must seed the sweep alike."""
+    import torch.distributed as dist
+
+    from .sampler import _draw_key
+
+    box = [_draw_key(rng) if dist.get_rank(group) == 0 else None]
+    dist.broadcast_object_list(box, src=0, group=group)
+    return int(box[0])
+
+
+def _sharded_handle(model, sampler, group=None):
+    from .sampler import _resampler_config
+
+    kind, thr = _resampler_config(sampler.resampler)
+    key = (id(model), sampler.kind, sampler.nparticles, kind, repr(thr))
+    h = _sharded.get(key)
+    if h is None:
+        if _sharded:
+            import torch.distributed as dist
+
+            dist.barrier(group=group)  # peers still map the old handle's stores: drop them together
+            _sharded.clear()
+        h = create_sharded_handle(model.model, sampler.nparticles, model.Y.shape[0], model.Y, resampler=kind,
+                                  ess_threshold=thr, group=group, sampler=sampler.kind)
+        h._model_keepalive = model
+        _sharded[key] = h
+    else:
+        h.set_observations(model.Y)
+    return h
+
+
+def sample(rng, model, sampler, n_iter=None, group=None):
+    """Sharded counterpart of ``sampler.sample`` (collective: every rank calls it with the same
+    arguments; only rank 0's ``rng`` is consumed). ``SMC`` -> SMCSample whose ``weights`` are this
+    rank's shard; ``PG`` / ``PGAS`` with ``n_iter`` -> list of PGSample (identical on every rank)."""
+    from . import sampler as S
+
+    if isinstance(sampler, S.SMC):
+        h = _sharded_handle(model, sampler, group)
+        logev = h.sweep(_shared_key(rng, group))
+        return S.SMCSample(h, model, h.weights_view(), logev)
+    if n_iter is None:
+        raise TypeError("sample(rng, model, PG|PGAS, n_iter): n_iter is required")
+    out, state = [], None
+    for _ in range(int(n_iter)):
+        smp, state = step(rng, model, sampler, state, group=group)
+        out.append(smp)
+    return out
+
+
+def step(rng, model, sampler, state=None, group=None):
+    """Sharded counterpart of ``sampler.step`` (src/smc.jl:101-129): one conditional sweep over all
+    ranks and the collective pick; every rank returns the same PGSample."""
+    from . import sampler as S
+
+    h = _sharded_handle(model, sampler, group)
+    key = _shared_key(rng, group)
+    if state is None:
+        logev = h.sweep(key)
+    elif state._handle is h:
+        logev = h.sweep(key, ref_on_device=True)
+    else:
+        logev = h.sweep(key, ref_traj=state.trajectory.model.X)
+    _, traj = h.pick_trajectory()
+    tr = S.Trace(S.TracedSSM(model.model, model.Y, traj))
+    return S.PGSample(tr, logev), S.PGState(tr, h)

@@ -264,10 +264,12 @@ def main():
         def e2e_step():
             return S.sample(rng, tssm, smc).weights
     else:
-        def e2e_step():  # same calls sample() makes, on this rank's shard
-            h.set_observations(Y)
-            h.sweep(int(rng.integers(0, 2**63)))
-            return h.weights_view()
+        del h
+        tssm = S.TracedSSM(model, Y)
+        smc = S.SMC(N_PARTICLES * world, S.resample_systematic)
+
+        def e2e_step():  # the sharded sampler surface: every rank gets its shard of the weights
+            return D.sample(rng, tssm, smc).weights
     for _ in range(args.warmup):
         e2e_step()
     barrier()
@@ -285,7 +287,7 @@ def main():
     d2h = wts.nbytes + 24
 
     # ---- roofline: per-launch CUDA events around every kernel of one sweep (same workload)
-    hp = S._handle_for(tssm, smc) if world == 1 else h
+    hp = S._handle_for(tssm, smc) if world == 1 else D._sharded_handle(tssm, smc)
     hp.sweep_profiled(MASTER_SEED)
     _, cls_ms, cls_n = hp.sweep_profiled(MASTER_SEED)
     names = ["k_propagate", "k_normalise", "k_resample", "k_pgas"]
@@ -331,7 +333,7 @@ def main():
                        "timing": "CUDA events on the library's stream around the replayed CUDA graph, max over ranks"},
             "logevidence": logev, "wall_s": wall,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "api": "sampler.sample(rng, TracedSSM(model, Y), SMC(N, resample_systematic)) -> SMCSample(weights, logevidence)"},
+                    "api": ("sampler.sample" if world == 1 else "distributed.sample") + "(rng, TracedSSM(model, Y), SMC(N, resample_systematic)) -> SMCSample(weights, logevidence)"},
             "gpu_launches": launches, "clocks": clk, "roofline": roofline,
         }
         if world == 1 and not args.no_cpu_baseline:

@@ -75,6 +75,27 @@ def main():
         h.close()
         checked += 1
 
+    # ---- the sampler surface, sharded: same chain as the single-handle oracle recursion
+    from advancedps_b200 import sampler as S
+
+    sv = models.stochastic_volatility()
+    _, Y = O.simulate_data(sv, T, 0xDA7A0004)
+    tssm = S.TracedSSM(sv, Y)
+    chain = D.sample(np.random.default_rng(5), tssm, S.PGAS(N), 3)
+    rng0 = np.random.default_rng(5)
+    cfg = _abi.make_config(sv, N, T, sampler=_abi.SAMPLER_PGAS, ess_threshold=1.0)
+    ref = None
+    for smp in chain:
+        key = int(rng0.integers(0, 2**64, dtype=np.uint64))
+        ro = O.sweep(cfg, Y, key, ref_traj=ref, mode=O.CANON)
+        _, ref = O.pick_trajectory(cfg, key, ro, mode=O.CANON)
+        assert smp.logevidence == ro.logevidence and np.array_equal(smp.trajectory.model.X, ref)
+    smc = D.sample(np.random.default_rng(6), S.TracedSSM(models.linear_gaussian(), Y), S.SMC(N, S.resample_systematic))
+    tot = torch.tensor([float(smc.weights.sum())], dtype=torch.float64, device="cuda")
+    dist.all_reduce(tot)
+    assert abs(float(tot.item()) - 1.0) < 1e-12
+    checked += 2
+
     dist.barrier()
     if rank == 0:
         print(f"MP_SHARDED_OK world={world} cases={checked}", flush=True)
