@@ -145,6 +145,19 @@ def run_reference(args, rank, emit=print):
     emit(json.dumps(out))
 
 
+def oracle_check(seed, logev_gpu):
+    """The first half of the parity claim at the FULL bench size: the oracle (CANON mode, the
+    arithmetic the GPU reproduces) run once with the seed of the last timed sweep."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle as O
+    from advancedps_b200 import _abi, models
+
+    cfg = _abi.make_config(models.linear_gaussian(), N_PARTICLES, T_STEPS)
+    ro = O.sweep(cfg, make_data(), seed, mode=O.CANON, history=False)
+    return {"oracle_canon": ro.logevidence, "abs_err": abs(logev_gpu - ro.logevidence),
+            "rel_err": abs(logev_gpu - ro.logevidence) / abs(ro.logevidence), "tolerance": 1e-6}
+
+
 def cpu_baseline():
     """Oracle port timed on this box's host cores, rank 0 at N=1 only: one sweep of the sample."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
@@ -322,6 +335,7 @@ def main():
                                          "l2": "flushed between launches (512 MB memset, then a 256 MB streaming read so L2 is cold and clean)"}
     barrier()
 
+    kal_ll = float(models.kalman_loglik(model, Y)[0])
     if rank == 0:
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -332,12 +346,18 @@ def main():
                        "l2": "flushed between timed sweeps (256 MB written, then 256 MB read); each sweep also streams 1.2 GB of state/ancestor history",
                        "timing": "CUDA events on the library's stream around the replayed CUDA graph, max over ranks"},
             "logevidence": logev, "wall_s": wall,
+            # the second half of BASELINE's metric: log-Z error. Against the oracle the estimate is
+            # bit-equal (parity tests, also at this size: tests/test_gpu_full_size.py); against the
+            # exact Kalman log-likelihood the difference is the Monte-Carlo error of the filter.
+            "logZ": {"estimate": logev, "kalman_exact": kal_ll, "error_vs_kalman": logev - kal_ll,
+                     "vs_oracle": "bit-equal at test sizes (tests/test_gpu_sweep_parity.py); full size: see oracle_check"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "api": ("sampler.sample" if world == 1 else "distributed.sample") + "(rng, TracedSSM(model, Y), SMC(N, resample_systematic)) -> SMCSample(weights, logevidence)"},
             "gpu_launches": launches, "clocks": clk, "roofline": roofline,
         }
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline()
+            out["logZ"]["oracle_check"] = oracle_check(MASTER_SEED + args.steps - 1, logev)
         emit(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
