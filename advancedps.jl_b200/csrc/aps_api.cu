@@ -87,11 +87,11 @@ static pgas_fn pick_pgas_select(int d) {
         default: return k_pgas_select<4>;
     }
 }
-static res_fn pick_resample(int kind, bool multi = false) {
-    if (multi) return kind == APS_RESAMPLE_STRATIFIED ? k_resample<APS_RESAMPLE_STRATIFIED, true>
-                                                      : k_resample<APS_RESAMPLE_SYSTEMATIC, true>;
-    return kind == APS_RESAMPLE_STRATIFIED ? k_resample<APS_RESAMPLE_STRATIFIED, false>
-                                           : k_resample<APS_RESAMPLE_SYSTEMATIC, false>;
+static res_fn pick_resample(int kind, bool multi = false, bool defer = false) {
+    const bool strat = kind == APS_RESAMPLE_STRATIFIED;
+    if (multi) return strat ? k_resample<APS_RESAMPLE_STRATIFIED, true, false> : k_resample<APS_RESAMPLE_SYSTEMATIC, true, false>;
+    if (defer) return strat ? k_resample<APS_RESAMPLE_STRATIFIED, false, true> : k_resample<APS_RESAMPLE_SYSTEMATIC, false, true>;
+    return strat ? k_resample<APS_RESAMPLE_STRATIFIED, false, false> : k_resample<APS_RESAMPLE_SYSTEMATIC, false, false>;
 }
 
 // ------------------------------------------------------------------ TMA descriptor of the integer-weight array
@@ -129,9 +129,10 @@ static int enable_k3_smem() {
     static bool done = false;
     if (done) return APS_OK;
     for (int kind : {APS_RESAMPLE_SYSTEMATIC, APS_RESAMPLE_STRATIFIED})
-        for (int multi = 0; multi < 2; ++multi) {
-            prefer_max_smem(pick_resample(kind, multi != 0));
-            CU(cudaFuncSetAttribute(pick_resample(kind, multi != 0), cudaFuncAttributeMaxDynamicSharedMemorySize, APS_K3_DYN_SMEM));
+        for (int variant = 0; variant < 3; ++variant) {
+            res_fn f = pick_resample(kind, variant == 1, variant == 2);
+            prefer_max_smem(f);
+            CU(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, APS_K3_DYN_SMEM));
         }
     prefer_max_smem(k_normalise<IN_LOGW>);
     prefer_max_smem(k_normalise<IN_W>);
@@ -355,6 +356,11 @@ extern "C" int aps_create(const aps_config *cfg, aps_handle **out) {
     c.fat_cnt = reinterpret_cast<int *>(reinterpret_cast<char *>(h->d_mail) + aps_mail_bytes());
     c.fat = reinterpret_cast<FatEntry *>(reinterpret_cast<char *>(h->d_mail) + aps_mail_bytes() + aps_fatcnt_bytes(c.fat_steps));
     c.fat_min = fat_min_for(N);
+    // deferred plan: one GPU, systematic / stratified, few enough tiles that every resample block can
+    // afford to sum them (<= 8 loads per thread and array)
+    c.defer_plan = (world == 1 && c.num_tiles <= 1024 && getenv("APS_NO_DEFER_PLAN") == nullptr &&
+                    (cfg->resampler == APS_RESAMPLE_SYSTEMATIC || cfg->resampler == APS_RESAMPLE_STRATIFIED))
+                       ? 1 : 0;
     if (world > 1) CUH(cudaMalloc(&h->d_peers, sizeof(PeerTable)));
     if (cfg->resampler == APS_RESAMPLE_MULTINOMIAL || cfg->resampler == APS_RESAMPLE_RESIDUAL) {
         CUH(cudaMalloc(&h->d_cum, sizeof(u64) * (size_t)c.NS));
@@ -381,7 +387,7 @@ extern "C" int aps_create(const aps_config *cfg, aps_handle **out) {
     c.sp = h->d_sp;
     h->f_prop = pick_propagate(cfg->model.obs_kind, d, cfg->model.dy, world > 1);
     prefer_max_smem(h->f_prop);
-    h->f_res = pick_resample(cfg->resampler, world > 1);
+    h->f_res = pick_resample(cfg->resampler, world > 1, c.defer_plan != 0);
     h->f_pmax = pick_pgas_max(d);
     h->f_psel = pick_pgas_select(d);
     prefer_max_smem(h->f_pmax);

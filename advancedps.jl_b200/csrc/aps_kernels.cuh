@@ -50,7 +50,7 @@ struct DevCtx {
     long long slot0;       // global index of this rank's first slot
     const PeerTable *peers; // device copy of the peer table, or null on one GPU
     int rank, world;
-    int dbg, pad2;         // diagnostics only (APS_DEBUG_MULTI): 1 skip waits, 2 skip sys fences, 4 local gathers, 8 local scatter
+    int dbg, defer_plan;   // defer_plan: one GPU, few tiles: k_resample derives totals / prefix / plan itself (k_normalise has no last-block phase); dbg: diagnostics only (APS_DEBUG_MULTI): 1 skip waits, 2 skip sys fences, 4 local gathers, 8 local scatter
     int *fat_cnt;          // [steps] entries in the fat-parent list of each decision point
     FatEntry *fat;         // [steps][APS_FAT_MAX]
     long long fat_steps;   // steps the lists are sized for (T + 2; 1 at the operator level)
@@ -289,6 +289,37 @@ __device__ __forceinline__ void make_plan(const DevCtx &c, long long s, double M
     p.pad = 0;
     *out = p;
 }
+// the two independent halves of make_plan, for callers that can run them on different warps
+// (same arithmetic, disjoint fields): A = weights summary and decision, B = resampling offsets
+template <int INPUT>
+__device__ __forceinline__ void make_plan_a(const DevCtx &c, long long s, double M, u64 Q, u64 Q1, u64 Q2, int err,
+                                            StepPlan *out) {
+    if (INPUT != IN_Q) {
+        if (!(M == M) || M == aps_bits2d(0x7FF0000000000000ULL) || M == aps_bits2d(0xFFF0000000000000ULL))
+            err = APS_ERR_WEIGHTS;
+        if (INPUT == IN_W && !(M > 0.0)) err = APS_ERR_WEIGHTS;
+    }
+    if (Q == 0 || Q2 == 0) err = APS_ERR_WEIGHTS;
+    out->M = M;
+    out->Q = Q;
+    out->logZ = M + aps_log((double)Q * aps_pow2i(-c.S));
+    const double ess = ((double)Q1 * (double)Q1) / (double)Q2;
+    out->ess = ess;
+    out->resampled = c.bare ? 1 : (ess <= c.ess_threshold * (double)c.Ng ? 1 : 0);
+    out->err = err;
+    out->pad = 0;
+}
+__device__ __forceinline__ void make_plan_b(const DevCtx &c, long long s, u64 Q, StepPlan *out) {
+    const long long n = c.n_override > 0 ? c.n_override : c.Ng - (c.sp->has_ref ? 1 : 0);
+    out->n = n;
+    uint64_t w0, w1;
+    aps_philox2x64(0, aps_ctr1((u64)(s + c.ctr_offset), APS_DOM_RESAMPLE, 0), c.sp->key, &w0, &w1);
+    const u64 R = ceil_uq53(aps_u53(w0), Q);
+    out->R = R;
+    out->ratio = 0x1.0p24 * ((double)n / (double)Q);
+    out->roff = 0x1.0p24 * ((double)R / (double)Q);
+    out->guard = 2 + (int)((n + (1LL << 25) - 1) >> 25);
+}
 // evidence bookkeeping, done once per decision point by the thread that records the plan
 __device__ __forceinline__ void record_plan(const DevCtx &c, long long s, const StepPlan &p) {
     if (c.st) {
@@ -392,6 +423,12 @@ __global__ void __launch_bounds__(APS_K2_THREADS) k_normalise(const __grid_const
         c.tile_sum[blockIdx.x] = s_tot[0];
         c.tile_s1[blockIdx.x] = s_tot[1];
         c.tile_s2[blockIdx.x] = s_tot[2];
+    }
+    // One GPU and few tiles (in-sweep, systematic / stratified): every block of k_resample sums the
+    // tile totals itself while its TMA load is in flight and derives the plan, so this kernel ends
+    // here -- no ticket, no serial last-block phase (3.4 us of 16 at N = 1e6).
+    if (c.defer_plan) return;
+    if (threadIdx.x == 0) {
         __threadfence();
         const unsigned ticket = atomicAdd(&acc->done_ctr, 1u);
         s_last = (ticket == gridDim.x - 1) ? 1u : 0u;
@@ -787,7 +824,7 @@ __device__ __forceinline__ int children_below_fast(u64 C, u64 Q, int n, double r
 // zero-filled by the hardware, so ragged tails need no special case.
 #define APS_TILE_BYTES (APS_TILE * 8)
 #define APS_K3_DYN_SMEM (APS_TILE_BYTES + APS_OWN_WORDS(APS_K3_CAP) * 4)
-template <int KIND, bool MULTI>
+template <int KIND, bool MULTI, bool DEFER>
 __global__ void __launch_bounds__(APS_K3_THREADS, MULTI ? APS_K3_MINBLOCKS - 2 : APS_K3_MINBLOCKS) k_resample(const __grid_constant__ DevCtx c, const long long s,
                                                              int32_t *__restrict__ anc_out,
                                                              const __grid_constant__ CUtensorMap tmap_q) {
@@ -828,7 +865,8 @@ __global__ void __launch_bounds__(APS_K3_THREADS, MULTI ? APS_K3_MINBLOCKS - 2 :
         roff = KIND == APS_RESAMPLE_SYSTEMATIC ? pp->roff : 0.0;
         key = KIND == APS_RESAMPLE_STRATIFIED ? c.sp->key : 0ull;
     };
-    if (!MULTI) {
+    constexpr bool defer = !MULTI && DEFER;
+    if (!MULTI && !defer) {
         if (!pp->resampled || pp->err) {
             identity_ancestors();
             return;
@@ -847,9 +885,62 @@ __global__ void __launch_bounds__(APS_K3_THREADS, MULTI ? APS_K3_MINBLOCKS - 2 :
 #endif
     }
     const u64 step = (u64)(s + c.ctr_offset);
-    u64 tprefix = c.tile_prefix[blockIdx.x];
+    u64 tprefix = 0;
+    if (!defer) tprefix = c.tile_prefix[blockIdx.x];
 
     zero_own<APS_K3_THREADS, APS_K3_CPT>(own);
+    if (defer) {
+        // Deferred plan (see k_normalise): while the TMA load is in flight, sum the tile totals
+        // (integers: any order), take the part below this tile as its prefix, and derive the plan of
+        // decision point s -- the same make_plan the normalise kernel's last block would have run.
+        __shared__ u64 s_acc4[4];
+        __shared__ StepPlan s_plan1;
+        if (tid < 4) s_acc4[tid] = 0;
+        __syncthreads();
+        const long long nt = c.num_tiles;
+        u64 t0 = 0, t1 = 0, t2 = 0, p0 = 0;
+        for (long long k = tid; k < nt; k += APS_K3_THREADS) {
+            const u64 v = __ldcg(&c.tile_sum[k]);
+            t0 += v;
+            if (k < (long long)blockIdx.x) p0 += v;
+            t1 += __ldcg(&c.tile_s1[k]);
+            t2 += __ldcg(&c.tile_s2[k]);
+        }
+        t0 = warp_sum_u64(t0);
+        t1 = warp_sum_u64(t1);
+        t2 = warp_sum_u64(t2);
+        p0 = warp_sum_u64(p0);
+        if ((tid & 31) == 0) {
+            atomicAdd(&s_acc4[0], t0);
+            atomicAdd(&s_acc4[1], t1);
+            atomicAdd(&s_acc4[2], t2);
+            atomicAdd(&s_acc4[3], p0);
+        }
+        __syncthreads();
+        if (tid == 0) {  // the two halves of the plan on two warps
+            const StepAcc *acc = &c.acc[s];
+            int err = acc->bad ? APS_ERR_WEIGHTS : 0;
+            if (acc->max_enc == 0) err = APS_ERR_WEIGHTS;
+            make_plan_a<IN_LOGW>(c, s, aps_decode_ordered(acc->max_enc), s_acc4[0], s_acc4[1], s_acc4[2], err, &s_plan1);
+            c.tile_prefix[blockIdx.x] = s_acc4[3];  // kept for the final pick (k_pick)
+        } else if (tid == 32) {
+            make_plan_b(c, s, s_acc4[0], &s_plan1);
+        }
+        __syncthreads();
+        if (blockIdx.x == 0 && tid == 0) record_plan(c, s, s_plan1);
+        pp = &s_plan1;
+        tprefix = s_acc4[3];
+        if (!pp->resampled || pp->err) {
+            if (tid < 32) {
+                __syncwarp();
+                mbar_wait(&mbar, 0);  // the tile is still landing in shared memory: do not leave before it has
+            }
+            __syncthreads();
+            identity_ancestors();
+            return;
+        }
+        load_plan();
+    }
     if (tid < 32) {  // one warp polls the mbarrier, the others park on the block barrier
         __syncwarp();
         mbar_wait(&mbar, 0);
