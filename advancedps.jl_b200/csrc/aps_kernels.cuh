@@ -979,16 +979,31 @@ __global__ void __launch_bounds__(APS_K3_THREADS, MULTI ? APS_K3_MINBLOCKS - 2 :
         if (!(c.dbg & 1) && !mail_wait(c.peers, c.rank, c.world, 1, step_seq(c, s), s_t, 4, c.st->spin)) s_okt = 0;
         if (c.dbg & 1) { if (tid < c.world) { s_t[tid][0] = 1ull << 50; s_t[tid][1] = 1ull << 30; s_t[tid][2] = 1ull << 40; s_t[tid][3] = c.acc[s].max_enc; } }
         __syncthreads();
-        if (tid == 0) {
-            u64 off;
-            multi_plan(c, s, s_t, s_okt != 0, &s_plan, &off);
-            s_off = off;
-            if (blockIdx.x == 0) {
-                c.acc[s].rank_off = off;
-                record_plan(c, s, s_plan);
+        if (tid == 0 || tid == 32) {  // the two halves of the plan on two warps (same arithmetic as multi_plan)
+            u64 Q = 0, Q1 = 0, Q2 = 0, off = 0;
+            int bad = 0;
+            for (int r = 0; r < c.world; ++r) {
+                if (r < c.rank) off += s_t[r][0];
+                Q += s_t[r][0];
+                Q1 += s_t[r][1];
+                Q2 += s_t[r][2] & 0x7FFFFFFFFFFFFFFFULL;
+                bad |= (int)(s_t[r][2] >> 63);
+            }
+            if (tid == 0) {
+                const u64 menc = s_t[0][3];
+                int err = (bad || menc == 0) ? APS_ERR_WEIGHTS : 0;
+                if (!s_okt) err = APS_ERR_COMM;
+                make_plan_a<IN_LOGW>(c, s, aps_decode_ordered(menc), Q, Q1, Q2, err, &s_plan);
+                s_off = off;
+            } else {
+                make_plan_b(c, s, Q, &s_plan);
             }
         }
         __syncthreads();
+        if (blockIdx.x == 0 && tid == 0) {
+            c.acc[s].rank_off = s_off;
+            record_plan(c, s, s_plan);
+        }
         pp = &s_plan;
         tprefix += s_off;
         if (!pp->resampled || pp->err) {
