@@ -89,6 +89,7 @@ static pgas_fn pick_pgas_select(int d) {
 }
 static res_fn pick_resample(int kind, bool multi = false, bool defer = false) {
     const bool strat = kind == APS_RESAMPLE_STRATIFIED;
+    if (multi && defer) return strat ? k_resample<APS_RESAMPLE_STRATIFIED, true, true> : k_resample<APS_RESAMPLE_SYSTEMATIC, true, true>;
     if (multi) return strat ? k_resample<APS_RESAMPLE_STRATIFIED, true, false> : k_resample<APS_RESAMPLE_SYSTEMATIC, true, false>;
     if (defer) return strat ? k_resample<APS_RESAMPLE_STRATIFIED, false, true> : k_resample<APS_RESAMPLE_SYSTEMATIC, false, true>;
     return strat ? k_resample<APS_RESAMPLE_STRATIFIED, false, false> : k_resample<APS_RESAMPLE_SYSTEMATIC, false, false>;
@@ -129,8 +130,8 @@ static int enable_k3_smem() {
     static bool done = false;
     if (done) return APS_OK;
     for (int kind : {APS_RESAMPLE_SYSTEMATIC, APS_RESAMPLE_STRATIFIED})
-        for (int variant = 0; variant < 3; ++variant) {
-            res_fn f = pick_resample(kind, variant == 1, variant == 2);
+        for (int variant = 0; variant < 4; ++variant) {
+            res_fn f = pick_resample(kind, (variant & 1) != 0, (variant & 2) != 0);
             prefer_max_smem(f);
             CU(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, APS_K3_DYN_SMEM));
         }
@@ -358,7 +359,7 @@ extern "C" int aps_create(const aps_config *cfg, aps_handle **out) {
     c.fat_min = fat_min_for(N);
     // deferred plan: one GPU, systematic / stratified, few enough tiles that every resample block can
     // afford to sum them (<= 8 loads per thread and array)
-    c.defer_plan = (world == 1 && c.num_tiles <= 1024 && getenv("APS_NO_DEFER_PLAN") == nullptr &&
+    c.defer_plan = (c.num_tiles <= 1024 && getenv("APS_NO_DEFER_PLAN") == nullptr &&
                     (cfg->resampler == APS_RESAMPLE_SYSTEMATIC || cfg->resampler == APS_RESAMPLE_STRATIFIED))
                        ? 1 : 0;
     if (world > 1) CUH(cudaMalloc(&h->d_peers, sizeof(PeerTable)));

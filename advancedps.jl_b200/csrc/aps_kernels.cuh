@@ -427,7 +427,13 @@ __global__ void __launch_bounds__(APS_K2_THREADS) k_normalise(const __grid_const
     // One GPU and few tiles (in-sweep, systematic / stratified): every block of k_resample sums the
     // tile totals itself while its TMA load is in flight and derives the plan, so this kernel ends
     // here -- no ticket, no serial last-block phase (3.4 us of 16 at N = 1e6).
-    if (c.defer_plan) return;
+    if (c.defer_plan) {
+        if (multi && blockIdx.x == 0 && threadIdx.x == 0) {  // what block 0 of k_resample publishes with the totals
+            acc->tot[3] = max_enc;
+            acc->pad1 = (acc->bad | bad_in) ? 1u : 0u;
+        }
+        return;
+    }
     if (threadIdx.x == 0) {
         __threadfence();
         const unsigned ticket = atomicAdd(&acc->done_ctr, 1u);
@@ -865,7 +871,7 @@ __global__ void __launch_bounds__(APS_K3_THREADS, MULTI ? APS_K3_MINBLOCKS - 2 :
         roff = KIND == APS_RESAMPLE_SYSTEMATIC ? pp->roff : 0.0;
         key = KIND == APS_RESAMPLE_STRATIFIED ? c.sp->key : 0ull;
     };
-    constexpr bool defer = !MULTI && DEFER;
+    constexpr bool defer = DEFER;
     if (!MULTI && !defer) {
         if (!pp->resampled || pp->err) {
             identity_ancestors();
@@ -892,7 +898,7 @@ __global__ void __launch_bounds__(APS_K3_THREADS, MULTI ? APS_K3_MINBLOCKS - 2 :
     if (defer) {
         // Deferred plan (see k_normalise): while the TMA load is in flight, sum the tile totals
         // (integers: any order), take the part below this tile as its prefix, and derive the plan of
-        // decision point s -- the same make_plan the normalise kernel's last block would have run.
+        // decision point s -- the same arithmetic the normalise kernel's last block would have run.
         __shared__ u64 s_acc4[4];
         __shared__ StepPlan s_plan1;
         if (tid < 4) s_acc4[tid] = 0;
@@ -917,29 +923,47 @@ __global__ void __launch_bounds__(APS_K3_THREADS, MULTI ? APS_K3_MINBLOCKS - 2 :
             atomicAdd(&s_acc4[3], p0);
         }
         __syncthreads();
-        if (tid == 0) {  // the two halves of the plan on two warps
-            const StepAcc *acc = &c.acc[s];
-            int err = acc->bad ? APS_ERR_WEIGHTS : 0;
-            if (acc->max_enc == 0) err = APS_ERR_WEIGHTS;
-            make_plan_a<IN_LOGW>(c, s, aps_decode_ordered(acc->max_enc), s_acc4[0], s_acc4[1], s_acc4[2], err, &s_plan1);
-            c.tile_prefix[blockIdx.x] = s_acc4[3];  // kept for the final pick (k_pick)
-        } else if (tid == 32) {
-            make_plan_b(c, s, s_acc4[0], &s_plan1);
-        }
-        __syncthreads();
-        if (blockIdx.x == 0 && tid == 0) record_plan(c, s, s_plan1);
-        pp = &s_plan1;
         tprefix = s_acc4[3];
-        if (!pp->resampled || pp->err) {
-            if (tid < 32) {
-                __syncwarp();
-                mbar_wait(&mbar, 0);  // the tile is still landing in shared memory: do not leave before it has
+        if (tid == 0) c.tile_prefix[blockIdx.x] = s_acc4[3];  // (local) prefix, kept for the final pick (k_pick)
+        if (MULTI) {
+            // sharded: these are the SHARD totals. Block 0 publishes them to every rank (all-gather,
+            // consumer side: the normalise kernel has no last block any more); the wait and the plan
+            // follow after the tile load and the local scan.
+            __shared__ u64 s_pub[4];
+            if (blockIdx.x == 0) {
+                if (tid == 0) {
+                    StepAcc *acc = &c.acc[s];
+                    s_pub[0] = acc->tot[0] = s_acc4[0];
+                    s_pub[1] = acc->tot[1] = s_acc4[1];
+                    s_pub[2] = acc->tot[2] = s_acc4[2] | ((u64)(acc->pad1 ? 1 : 0) << 63);  // NaN flag (left by k_normalise)
+                    s_pub[3] = acc->tot[3];                                                 // global maximum (left by k_normalise)
+                }
+                __syncthreads();
+                mail_post(c.peers, c.rank, c.world, 1, step_seq(c, s), s_pub, 4);
+            }
+        } else {
+            if (tid == 0) {  // the two halves of the plan on two warps
+                const StepAcc *acc = &c.acc[s];
+                int err = acc->bad ? APS_ERR_WEIGHTS : 0;
+                if (acc->max_enc == 0) err = APS_ERR_WEIGHTS;
+                make_plan_a<IN_LOGW>(c, s, aps_decode_ordered(acc->max_enc), s_acc4[0], s_acc4[1], s_acc4[2], err, &s_plan1);
+            } else if (tid == 32) {
+                make_plan_b(c, s, s_acc4[0], &s_plan1);
             }
             __syncthreads();
-            identity_ancestors();
-            return;
+            if (blockIdx.x == 0 && tid == 0) record_plan(c, s, s_plan1);
+            pp = &s_plan1;
+            if (!pp->resampled || pp->err) {
+                if (tid < 32) {
+                    __syncwarp();
+                    mbar_wait(&mbar, 0);  // the tile is still landing in shared memory: do not leave before it has
+                }
+                __syncthreads();
+                identity_ancestors();
+                return;
+            }
+            load_plan();
         }
-        load_plan();
     }
     if (tid < 32) {  // one warp polls the mbarrier, the others park on the block barrier
         __syncwarp();
