@@ -458,7 +458,10 @@ static long long enqueue_sweep(aps_handle *h, LaunchProf *prof = nullptr) {
     const int gt = (int)c.num_tiles;
     // one thread per slot pair, grid-stride over at most 5 resident blocks per SM
     long long gk1l = ((c.N + 1) / 2 + APS_K1_THREADS - 1) / APS_K1_THREADS;
-    if (gk1l > (long long)sm_count() * 5) gk1l = (long long)sm_count() * 5;
+#ifndef APS_K1_GRID_PER_SM
+#define APS_K1_GRID_PER_SM 5
+#endif
+    if (gk1l > (long long)sm_count() * APS_K1_GRID_PER_SM) gk1l = (long long)sm_count() * APS_K1_GRID_PER_SM;
     const int gk1 = (int)gk1l;
     // slab addressing is resolved here, once per launch (no 64-bit modulo in the kernels)
     auto x_slab = [&](long long t) { return c.x + ((t - 1 + c.x_slabs) % c.x_slabs) * (long long)c.d * c.NS; };

@@ -91,8 +91,13 @@ __global__ void k_init_sweep(const __grid_constant__ DevCtx c) {
 // One thread per PAIR of adjacent slots (2p, 2p+1): the pair shares D Philox blocks and their
 // Box-Muller normals (aps_pair_normals), ancestors / log-weights / states move as 8- and 16-byte
 // vectors. Block maxima of the new log-weights are folded into one atomicMax per block.
+#ifdef APS_K1_MINBLOCKS   // tuning experiments only (csrc/build.sh -DAPS_K1_MINBLOCKS=6); the default leaves it to ptxas
+#define APS_K1_BOUNDS __launch_bounds__(APS_K1_THREADS, APS_K1_MINBLOCKS)
+#else
+#define APS_K1_BOUNDS __launch_bounds__(APS_K1_THREADS)
+#endif
 template <int D, int DY, int OBS, bool MULTI>
-__global__ void __launch_bounds__(APS_K1_THREADS) k_propagate(const __grid_constant__ DevCtx c, const long long t,
+__global__ void APS_K1_BOUNDS k_propagate(const __grid_constant__ DevCtx c, const long long t,
                                                            double *__restrict__ xt, const double *__restrict__ xp,
                                                            const int32_t *anc) {  // not __restrict__: patched below
     __shared__ u64 red[APS_K1_THREADS / 32];
