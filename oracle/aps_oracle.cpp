@@ -39,10 +39,41 @@
 #include <math.h>
 #include <vector>
 #include <algorithm>
+#include <thread>
 
 #include "../include/aps_b200.h"
 
 typedef unsigned __int128 u128;
+
+/* Threads. The reference sweep is serial (src/container.jl:194,264) and so is this oracle by
+ * default. orc_set_threads(n > 1) lets the particle-parallel loops of the CANON mode (advance,
+ * quantise, integer sums, maxima) run on n threads: every one of them is either independent per
+ * particle or an exact integer / max reduction over per-thread partials, so results are
+ * bit-identical for any n. It exists only to give bench.py an all-cores CPU figure next to the
+ * single-thread one; the SEQ mode (sequential fp64 sums, the reference's order) and the
+ * resampling walks stay serial. (std::thread: the image has no OpenMP runtime.)                 */
+static int g_threads = 1;
+extern "C" void orc_set_threads(int n) { g_threads = n < 1 ? 1 : (n > 256 ? 256 : n); }
+extern "C" int orc_max_threads(void) {
+    unsigned n = std::thread::hardware_concurrency();
+    return n ? (int)n : 1;
+}
+/* f(lo, hi, k): chunk k of [0, n) */
+template <class F>
+static void pfor(int64_t n, F f) {
+    const int nt = (g_threads > 1 && n >= 4096) ? g_threads : 1;
+    if (nt == 1) {
+        f((int64_t)0, n, 0);
+        return;
+    }
+    std::vector<std::thread> th;
+    const int64_t per = (n + nt - 1) / nt;
+    for (int k = 0; k < nt; ++k) {
+        const int64_t lo = (int64_t)k * per, hi = std::min(n, lo + per);
+        if (lo < hi) th.emplace_back([=] { f(lo, hi, k); });
+    }
+    for (auto &t : th) t.join();
+}
 
 enum { ORC_SEQ = 0, ORC_CANON = 1 };
 
@@ -62,10 +93,23 @@ int orc_ess_shift(int64_t n) { return aps_ess_shift((uint64_t)n); }
 
 /* ------------------------------------------------------------------ weights (src/container.jl:95-119) */
 static double max_of(const double *x, int64_t n) {
+    double part[256];
+    int nanp[256];
+    for (int k = 0; k < 256; ++k) { part[k] = -INFINITY; nanp[k] = 0; }
+    pfor(n, [&](int64_t lo, int64_t hi, int k) {
+        double m = -INFINITY;
+        int nan = 0;
+        for (int64_t i = lo; i < hi; ++i) {
+            if (x[i] != x[i]) nan = 1;
+            else if (x[i] > m) m = x[i];
+        }
+        part[k] = m;
+        nanp[k] = nan;
+    });
     double m = -INFINITY;
-    for (int64_t i = 0; i < n; ++i) {
-        if (x[i] != x[i]) return NAN;
-        if (x[i] > m) m = x[i];
+    for (int k = 0; k < 256; ++k) {
+        if (nanp[k]) return NAN;
+        if (part[k] > m) m = part[k];
     }
     return m;
 }
@@ -122,12 +166,19 @@ static double canon_logsum(uint64_t Q, int S) { return aps_log((double)Q * aps_p
 
 static double canon_ess(const uint64_t *q, int64_t n) {
     int h = aps_ess_shift((uint64_t)n);
+    uint64_t p1[256] = {0}, p2[256] = {0};
+    pfor(n, [&](int64_t lo, int64_t hi, int k) {
+        uint64_t a = 0, b = 0;
+        for (int64_t i = lo; i < hi; ++i) {
+            uint64_t t = q[i] >> h;
+            a += t;
+            b += t * t;
+        }
+        p1[k] = a;
+        p2[k] = b;
+    });
     uint64_t s1 = 0, s2 = 0;
-    for (int64_t i = 0; i < n; ++i) {
-        uint64_t t = q[i] >> h;
-        s1 += t;
-        s2 += t * t;
-    }
+    for (int k = 0; k < 256; ++k) { s1 += p1[k]; s2 += p2[k]; }
     return ((double)s1 * (double)s1) / (double)s2;
 }
 
@@ -481,7 +532,8 @@ void advance_all(Sweep &sw, int64_t t) { /* reweight!: src/container.jl:259-302 
     double *xt = sw.x_hist + (size_t)(t - 1) * N * D;
     const double *xp_all = t > 1 ? sw.x_hist + (size_t)(t - 2) * N * D : nullptr;
     const int32_t *anc = sw.anc_hist + (size_t)(t - 1) * N;
-    for (int64_t i = 0; i < N; ++i) {
+    pfor(N, [&](int64_t lo_i, int64_t hi_i, int) {
+    for (int64_t i = lo_i; i < hi_i; ++i) {
         double x[D];
         if (hasref && i == N - 1) {
             for (int k = 0; k < D; ++k) x[k] = sw.ref[(size_t)(t - 1) * D + k]; /* pgas.jl:69-72 */
@@ -499,6 +551,7 @@ void advance_all(Sweep &sw, int64_t t) { /* reweight!: src/container.jl:259-302 
         for (int k = 0; k < D; ++k) xt[(size_t)i * D + k] = x[k];
         sw.logw[(size_t)i] += aps_obs_logpdf<D, DY, OBS>(&sw.md, x, y); /* increase_logweight!, container.jl:279 */
     }
+    });
 }
 
 typedef void (*advance_fn)(Sweep &, int64_t);
@@ -533,11 +586,17 @@ double refresh_weights(Sweep &sw) {
     sw.M = m;
     if (m != m || m == -INFINITY || m == INFINITY) { sw.err = 2; return NAN; }
     if (sw.mode == ORC_CANON) {
+        uint64_t part[256] = {0};
+        pfor(N, [&](int64_t lo, int64_t hi, int k) {
+            uint64_t a = 0;
+            for (int64_t i = lo; i < hi; ++i) {
+                sw.q[(size_t)i] = aps_quantise(aps_exp(sw.logw[(size_t)i] - m), sw.S);
+                a += sw.q[(size_t)i];
+            }
+            part[k] = a;
+        });
         uint64_t Q = 0;
-        for (int64_t i = 0; i < N; ++i) {
-            sw.q[(size_t)i] = aps_quantise(aps_exp(sw.logw[(size_t)i] - m), sw.S);
-            Q += sw.q[(size_t)i];
-        }
+        for (int k = 0; k < 256; ++k) Q += part[k];
         sw.Q = Q;
         if (Q == 0) { sw.err = 2; return NAN; }
         return canon_ess(sw.q.data(), N);
@@ -554,8 +613,14 @@ double current_logZ(Sweep &sw) { /* logZ(pc), src/container.jl:109 */
     double m = max_of(sw.logw.data(), N);
     if (m != m || m == -INFINITY) { sw.err = 2; return NAN; }
     if (sw.mode == ORC_CANON) {
+        uint64_t part[256] = {0};
+        pfor(N, [&](int64_t lo, int64_t hi, int k) {
+            uint64_t a = 0;
+            for (int64_t i = lo; i < hi; ++i) a += aps_quantise(aps_exp(sw.logw[(size_t)i] - m), sw.S);
+            part[k] = a;
+        });
         uint64_t Q = 0;
-        for (int64_t i = 0; i < N; ++i) Q += aps_quantise(aps_exp(sw.logw[(size_t)i] - m), sw.S);
+        for (int k = 0; k < 256; ++k) Q += part[k];
         return m + canon_logsum(Q, sw.S);
     }
     double s = 0.0;

@@ -56,6 +56,16 @@ def _ptr(a):
 
 
 # ------------------------------------------------------------------ math
+def set_threads(n):
+    """OpenMP threads for the particle-parallel loops of the CANON mode (bit-identical results for
+    any n); 1 = the serial sweep of the reference. Returns the previous setting's maximum."""
+    lib().orc_set_threads(int(n))
+
+
+def max_threads():
+    return int(lib().orc_max_threads())
+
+
 def philox2x64(c0, c1, key):
     out = np.zeros(2, dtype=np.uint64)
     lib().orc_philox2x64(C.c_uint64(c0), C.c_uint64(c1), C.c_uint64(key), _ptr(out))

@@ -220,3 +220,21 @@ def test_not_normalisable_weights():
     with pytest.raises(O.OracleError) as e:
         O.sweep(cfg, np.full((2, 1), -np.inf), 1)
     assert e.value.code == 2
+
+
+def test_threaded_oracle_is_bit_identical():
+    """The oracle's optional threads (bench.py's all-cores figure) only split particle-independent
+    loops and exact integer / max reductions: same results for any thread count."""
+    m = models.linear_gaussian()
+    N, T = 20000, 6
+    _, Y = O.simulate_data(m, T, 3)
+    cfg = _abi.make_config(m, N, T, ess_threshold=0.5)
+    a = O.sweep(cfg, Y, 11, mode=O.CANON)
+    O.set_threads(4)
+    try:
+        b = O.sweep(cfg, Y, 11, mode=O.CANON)
+    finally:
+        O.set_threads(1)
+    assert a.logevidence == b.logevidence
+    assert np.array_equal(a.x_hist, b.x_hist) and np.array_equal(a.anc_hist, b.anc_hist)
+    assert np.array_equal(a.ess, b.ess) and np.array_equal(a.final_w, b.final_w)
