@@ -10,7 +10,7 @@ from ._abi import (  # noqa: F401
     SAMPLER_PG, SAMPLER_PGAS, SAMPLER_SMC,
 )
 from .sampler import (  # noqa: F401,E402
-    DEFAULT_RESAMPLER, PG, PGAS, SMC, ApsError, ParticleContainer, PGSample, PGState, ResampleWithESSThreshold,
+    DEFAULT_RESAMPLER, PG, PGAS, SMC, ApsError, DeviceParticleContainer, ParticleContainer, PGSample, PGState, ResampleWithESSThreshold,
     SMCSample, Trace, TracedSSM, effectiveSampleSize, getweight, getweights, increase_logweight_, logZ, randcat,
     resample_multinomial, resample_propagate_, resample_residual, resample_stratified, resample_systematic,
     reset_logweights_, reweight_, sample, step, sweep_,

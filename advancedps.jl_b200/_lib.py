@@ -21,6 +21,8 @@ EXPORTS = [
     "aps_create", "aps_destroy", "aps_set_observations", "aps_sweep", "aps_sweep_profiled",
     "aps_pick_trajectory",
     "aps_get_weights", "aps_get_weights_view", "aps_get_logweights", "aps_get_final_states", "aps_get_trajectory",
+    "aps_get_trajectories", "aps_pc_begin", "aps_pc_resample_propagate", "aps_pc_reweight", "aps_pc_logz",
+    "aps_set_logweights",
     "aps_get_step_stats", "aps_get_states", "aps_get_ancestors", "aps_get_fat_counts", "aps_smoothing_mean", "aps_last_sweep_ms",
     "aps_last_sweep_launches", "aps_resample", "aps_logsumexp", "aps_softmax", "aps_ess",
     "aps_randcat", "aps_bench_resample", "aps_ipc_export", "aps_ipc_import", "aps_last_error",
@@ -90,6 +92,11 @@ class Handle:
         # N: slots held by this handle (the local shard when world_size > 1); Ng: global particle count
         self.Ng, self.rank, self.world = cfg.n_particles, cfg.rank, cfg.world_size
         self.N, self.T, self.d, self.dy = cfg.n_particles // cfg.world_size, cfg.n_steps, cfg.model.d, cfg.model.dy
+        # generation: bumped by every call that overwrites the particle store (sweep / pc_begin), so
+        # lazily materialised results can tell that they went stale; ref_token: bumped whenever the
+        # device-resident reference trajectory is replaced (a pick, or a sweep given a host trajectory)
+        self.generation = 0
+        self.ref_token = 0
 
     def close(self):
         if self._h:
@@ -119,11 +126,13 @@ class Handle:
 
     def sweep(self, seed, ref_traj=None, ref_on_device=False):
         le = C.c_double()
+        self.generation += 1
         if ref_on_device:
             ref = C.c_void_p(1)
         elif ref_traj is not None:
             self._ref_keep = np.ascontiguousarray(ref_traj, dtype=np.float64).reshape(self.T, self.d)
             ref = ptr(self._ref_keep)
+            self.ref_token += 1
         else:
             ref = None
         check(lib().aps_sweep(self._h, C.c_uint64(seed), ref, C.byref(le)))
@@ -133,6 +142,7 @@ class Handle:
         """Unconditional sweep with per-launch CUDA events; returns (logevidence, ms[4], launches[4])
         for the {propagate, normalise, resample, pgas} kernel classes."""
         le = C.c_double()
+        self.generation += 1
         ms = (C.c_float * 4)()
         nl = (C.c_int64 * 4)()
         check(lib().aps_sweep_profiled(self._h, C.c_uint64(seed), None, C.byref(le), ms, nl))
@@ -141,11 +151,12 @@ class Handle:
     def pick_trajectory(self, want_traj=True):
         traj = np.zeros((self.T, self.d)) if want_traj else None
         slot = C.c_int64()
+        self.ref_token += 1
         check(lib().aps_pick_trajectory(self._h, ptr(traj), C.byref(slot)))
         return slot.value, traj
 
     def weights(self):
-        w = np.zeros(self.N)
+        w = np.empty(self.N)
         check(lib().aps_get_weights(self._h, ptr(w)))
         return w
 
@@ -172,6 +183,45 @@ class Handle:
         traj = np.zeros((self.T, self.d))
         check(lib().aps_get_trajectory(self._h, C.c_int64(slot), ptr(traj)))
         return traj
+
+    def trajectories(self):
+        """All N trajectories of the final particle set, (T, N, d) -- collect(pc) of SMCSample (src/smc.jl:56)."""
+        out = np.zeros((self.T, self.N, self.d))
+        check(lib().aps_get_trajectories(self._h, ptr(out)))
+        return out
+
+    # ---- container level: the device ParticleContainer driven call by call (src/container.jl:171-363)
+    def pc_begin(self, seed, ref_traj=None, ref_on_device=False):
+        self.generation += 1
+        if ref_on_device:
+            ref = C.c_void_p(1)
+        elif ref_traj is not None:
+            self._ref_keep = np.ascontiguousarray(ref_traj, dtype=np.float64).reshape(self.T, self.d)
+            ref = ptr(self._ref_keep)
+            self.ref_token += 1
+        else:
+            ref = None
+        check(lib().aps_pc_begin(self._h, C.c_uint64(seed), ref))
+
+    def pc_resample_propagate(self):
+        r = C.c_int32()
+        check(lib().aps_pc_resample_propagate(self._h, C.byref(r)))
+        return bool(r.value)
+
+    def pc_reweight(self):
+        d = C.c_int32()
+        check(lib().aps_pc_reweight(self._h, C.byref(d)))
+        return bool(d.value)
+
+    def pc_logZ(self):
+        z = C.c_double()
+        check(lib().aps_pc_logz(self._h, C.byref(z)))
+        return z.value
+
+    def set_logweights(self, logw):
+        logw = np.ascontiguousarray(logw, dtype=np.float64)
+        assert logw.shape == (self.N,)
+        check(lib().aps_set_logweights(self._h, ptr(logw)))
 
     def step_stats(self):
         logz = np.zeros(self.T)

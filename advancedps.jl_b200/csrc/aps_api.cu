@@ -162,6 +162,8 @@ static void preload_kernels() {
     cudaFuncGetAttributes(&a, k_plan_multi);
     cudaFuncGetAttributes(&a, k_fill_fat);
     cudaFuncGetAttributes(&a, k_smooth_step);
+    cudaFuncGetAttributes(&a, k_traj_step);
+    cudaFuncGetAttributes(&a, k_pc_provisional);
     cudaGetLastError();
     done = true;
 }
@@ -224,6 +226,9 @@ struct aps_handle {
     unsigned long long epoch, pick_seq;
     float last_ms;
     long long last_launches, graph_nodes;
+    // stepwise container (aps_pc_*): reweights done so far, decision points settled so far
+    bool pc_active;
+    long long pc_t, pc_decided;
     CUtensorMap tmap_q;
     prop_fn f_prop;
     res_fn f_res;
@@ -362,7 +367,13 @@ extern "C" int aps_create(const aps_config *cfg, aps_handle **out) {
     c.defer_plan = (c.num_tiles <= 1024 && getenv("APS_NO_DEFER_PLAN") == nullptr &&
                     (cfg->resampler == APS_RESAMPLE_SYSTEMATIC || cfg->resampler == APS_RESAMPLE_STRATIFIED))
                        ? 1 : 0;
-    if (world > 1) CUH(cudaMalloc(&h->d_peers, sizeof(PeerTable)));
+    if (world > 1) {
+        CUH(cudaMalloc(&h->d_peers, sizeof(PeerTable)));
+        if (const char *e = getenv("APS_COMM_TIMEOUT_MS")) {  // spin budget of one exchange wait (default 3000 ms)
+            const long long cyc = atoll(e) * 2000000LL;
+            if (cyc > 0) CUH(cudaMemcpyToSymbol(g_spin_limit, &cyc, sizeof(cyc)));
+        }
+    }
     if (cfg->resampler == APS_RESAMPLE_MULTINOMIAL || cfg->resampler == APS_RESAMPLE_RESIDUAL) {
         CUH(cudaMalloc(&h->d_cum, sizeof(u64) * (size_t)c.NS));
         CUH(cudaMalloc(&h->d_cut, sizeof(unsigned short) * (size_t)c.num_tiles * APS_CUT));
@@ -434,105 +445,133 @@ struct LaunchProf {
     }
 };
 
-// enqueue every kernel of one sweep on the handle's stream; returns the number of launches
-static long long enqueue_sweep(aps_handle *h, LaunchProf *prof = nullptr) {
-    const DevCtx &c = h->ctx;
-    cudaStream_t st = h->stream;
-    long long n = 0;
-#define APS_LAUNCH(cls_, ...)            \
-    do {                                 \
-        if (prof) prof->begin(cls_);     \
-        __VA_ARGS__;                     \
-        if (prof) prof->end();           \
-        ++n;                             \
+// the kernels of decision point t (resample_propagate! after the t-th reweight!): the resampler of
+// the handle and, for PGAS, the ancestor draw. `c` may differ from h->ctx (stepwise container).
+struct Launcher {
+    LaunchProf *prof;
+    long long n;
+    void begin(int cls) { if (prof) prof->begin(cls); }
+    void end() { if (prof) prof->end(); ++n; }
+};
+#define APS_LAUNCH(cls_, ...) \
+    do {                      \
+        L.begin(cls_);        \
+        __VA_ARGS__;          \
+        L.end();              \
     } while (0)
-    cudaMemsetAsync(c.acc, 0, sizeof(StepAcc) * (size_t)(c.T + 2), st);
-    cudaMemsetAsync(c.fat_cnt, 0, sizeof(int) * (size_t)c.fat_steps, st);
-    if (h->d_rs) {
-        cudaMemsetAsync(h->d_rs, 0, sizeof(ResidualState) * (size_t)(c.T + 2), st);
-        cudaMemsetAsync(h->d_done2, 0, sizeof(unsigned) * (size_t)(c.T + 2), st);
-    }
-    k_init_sweep<<<1, 32, 0, st>>>(c);
-    ++n;
-    const int gp = stride_grid(c.N);
-    const int gt = (int)c.num_tiles;
+
+static double *x_slab_of(const DevCtx &c, long long t) { return c.x + ((t - 1 + c.x_slabs) % c.x_slabs) * (long long)c.d * c.NS; }
+static int32_t *anc_slab_of(const DevCtx &c, long long sidx) { return c.anc + ((sidx + c.anc_slabs) % c.anc_slabs) * c.NS; }
+
+static void launch_propagate(aps_handle *h, const DevCtx &c, long long t, Launcher &L) {
+    cudaStream_t st = h->stream;
     // one thread per slot pair, grid-stride over at most 5 resident blocks per SM
     long long gk1l = ((c.N + 1) / 2 + APS_K1_THREADS - 1) / APS_K1_THREADS;
 #ifndef APS_K1_GRID_PER_SM
 #define APS_K1_GRID_PER_SM 5
 #endif
     if (gk1l > (long long)sm_count() * APS_K1_GRID_PER_SM) gk1l = (long long)sm_count() * APS_K1_GRID_PER_SM;
-    const int gk1 = (int)gk1l;
     // slab addressing is resolved here, once per launch (no 64-bit modulo in the kernels)
-    auto x_slab = [&](long long t) { return c.x + ((t - 1 + c.x_slabs) % c.x_slabs) * (long long)c.d * c.NS; };
-    auto anc_slab = [&](long long sidx) { return c.anc + ((sidx + c.anc_slabs) % c.anc_slabs) * c.NS; };
-    for (long long t = 1; t <= c.T; ++t) {
-        APS_LAUNCH(0, h->f_prop<<<gk1, APS_K1_THREADS, 0, st>>>(c, t, x_slab(t), x_slab(t - 1), anc_slab(t - 1)));
-        APS_LAUNCH(1, k_normalise<IN_LOGW><<<gt, APS_K2_THREADS, 0, st>>>(c, c.logw, t));
-        if (c.resampler == APS_RESAMPLE_SYSTEMATIC || c.resampler == APS_RESAMPLE_STRATIFIED) {
-            APS_LAUNCH(2, h->f_res<<<gt, APS_K3_THREADS, APS_K3_DYN_SMEM, st>>>(c, t, anc_slab(t), h->tmap_q));
-        } else {
-            const bool multi = c.world > 1;
-            MultiArgs a;
-            memset(&a, 0, sizeof(a));
-            a.cum = h->d_cum;
-            a.cut = h->d_cut;
-            a.cut_sh = h->d_cut_sh;
-            a.counts = h->d_counts;
-            a.tile_count = h->d_tile_count;
-            a.tile_cprefix = h->d_tile_cprefix;
-            a.tile_prefix = c.tile_prefix;
-            a.plan = c.plan + t;
-            a.N = c.N;
-            a.num_tiles = c.num_tiles;
-            a.step = t;
-            // sharded: the plan of this decision point comes from the exchanged shard totals
+    APS_LAUNCH(0, h->f_prop<<<(int)gk1l, APS_K1_THREADS, 0, st>>>(c, t, x_slab_of(c, t), x_slab_of(c, t - 1), anc_slab_of(c, t - 1)));
+}
+
+static void launch_decision(aps_handle *h, const DevCtx &c, long long t, res_fn f_res, Launcher &L) {
+    cudaStream_t st = h->stream;
+    const int gp = stride_grid(c.N);
+    const int gt = (int)c.num_tiles;
+    if (c.resampler == APS_RESAMPLE_SYSTEMATIC || c.resampler == APS_RESAMPLE_STRATIFIED) {
+        APS_LAUNCH(2, f_res<<<gt, APS_K3_THREADS, APS_K3_DYN_SMEM, st>>>(c, t, anc_slab_of(c, t), h->tmap_q));
+    } else {
+        const bool multi = c.world > 1;
+        MultiArgs a;
+        memset(&a, 0, sizeof(a));
+        a.cum = h->d_cum;
+        a.cut = h->d_cut;
+        a.cut_sh = h->d_cut_sh;
+        a.counts = h->d_counts;
+        a.tile_count = h->d_tile_count;
+        a.tile_cprefix = h->d_tile_cprefix;
+        a.tile_prefix = c.tile_prefix;
+        a.plan = c.plan + t;
+        a.N = c.N;
+        a.num_tiles = c.num_tiles;
+        a.step = t;
+        // sharded: the plan of this decision point comes from the exchanged shard totals
+        if (multi) {
+            APS_LAUNCH(2, k_plan_multi<<<1, 32, 0, st>>>(c, t));
+            a.child_off = &c.acc[t].child_off;
+        }
+        if (c.resampler == APS_RESAMPLE_MULTINOMIAL) {
+            a.qsrc = c.q;
+            a.wplan = c.plan + t;
+            a.n_draws = &c.plan[t].n;
             if (multi) {
-                APS_LAUNCH(2, k_plan_multi<<<1, 32, 0, st>>>(c, t));
-                a.child_off = &c.acc[t].child_off;
+                a.range_lo = &c.acc[t].rank_off;
+                a.range_len = &c.acc[t].tot[0];
             }
-            if (c.resampler == APS_RESAMPLE_MULTINOMIAL) {
-                a.qsrc = c.q;
-                a.wplan = c.plan + t;
-                a.n_draws = &c.plan[t].n;
-                if (multi) {
-                    a.range_lo = &c.acc[t].rank_off;
-                    a.range_len = &c.acc[t].tot[0];
-                }
-                cudaMemsetAsync(h->d_counts, 0, sizeof(int) * (size_t)c.N, st);
-            } else {
-                a.qsrc = h->d_rq;
-                a.wplan = c.plan + c.T + 1;
-                a.n_draws = &h->d_rs[t].n_rest;
-                if (multi) {
-                    a.range_lo = &h->d_rs[t].q_off;
-                    a.range_len = &h->d_rs[t].q_local;
-                }
-                APS_LAUNCH(2, k_residual_split<<<gt, APS_THREADS, 0, st>>>(a, c.q, h->d_rq, h->d_rs + t));
-                if (multi) APS_LAUNCH(2, k_residual_exchange<0><<<1, 32, 0, st>>>(c, t, c.plan + t, h->d_rs + t, c.plan + c.T + 1));
-                APS_LAUNCH(2, k_residual_weights<<<gt, APS_THREADS, 0, st>>>(a, h->d_rq, h->d_rs + t, c.tile_sum, c.tile_prefix,
-                                                                           c.plan + c.T + 1, h->d_done2 + t, &c.st->err));
-                if (multi) APS_LAUNCH(2, k_residual_exchange<1><<<1, 32, 0, st>>>(c, t, c.plan + t, h->d_rs + t, c.plan + c.T + 1));
+            cudaMemsetAsync(h->d_counts, 0, sizeof(int) * (size_t)c.N, st);
+        } else {
+            a.qsrc = h->d_rq;
+            a.wplan = c.plan + c.T + 1;
+            a.n_draws = &h->d_rs[t].n_rest;
+            if (multi) {
+                a.range_lo = &h->d_rs[t].q_off;
+                a.range_len = &h->d_rs[t].q_local;
             }
-            APS_LAUNCH(2, k_cumsum<<<gt, APS_THREADS, 0, st>>>(a));
-            // sharded: every rank makes all Ng draws and keeps those in its own weight range
-            const int gs = stride_grid((c.Ng + 1) / 2);
-            APS_LAUNCH(2, k_multi_search<1><<<gs, APS_K1_THREADS, 0, st>>>(a, &h->d_sp->key));
-            APS_LAUNCH(2, k_tile_counts<<<gt, APS_THREADS, 0, st>>>(a));
-            APS_LAUNCH(2, k_scan_tile_counts<<<1, APS_THREADS, 0, st>>>(a, nullptr, c, t));
-            APS_LAUNCH(2, k_expand_counts<<<gt, APS_THREADS, 0, st>>>(a, anc_slab(t), 1, c, t));
+            APS_LAUNCH(2, k_residual_split<<<gt, APS_THREADS, 0, st>>>(a, c.q, h->d_rq, h->d_rs + t));
+            if (multi) APS_LAUNCH(2, k_residual_exchange<0><<<1, 32, 0, st>>>(c, t, c.plan + t, h->d_rs + t, c.plan + c.T + 1));
+            APS_LAUNCH(2, k_residual_weights<<<gt, APS_THREADS, 0, st>>>(a, h->d_rq, h->d_rs + t, c.tile_sum, c.tile_prefix,
+                                                                       c.plan + c.T + 1, h->d_done2 + t, &c.st->err));
+            if (multi) APS_LAUNCH(2, k_residual_exchange<1><<<1, 32, 0, st>>>(c, t, c.plan + t, h->d_rs + t, c.plan + c.T + 1));
         }
-        if (c.sampler == APS_PGAS && t >= 2 && t <= c.T - 1) {
-            APS_LAUNCH(3, h->f_pmax<<<gp, APS_K1_THREADS, 0, st>>>(c, t, x_slab(t - 1), anc_slab(t - 1), anc_slab(t)));
-            APS_LAUNCH(3, h->f_psel<<<gt, APS_THREADS, 0, st>>>(c, t, x_slab(t - 1), anc_slab(t - 1), anc_slab(t)));
-        }
+        APS_LAUNCH(2, k_cumsum<<<gt, APS_THREADS, 0, st>>>(a));
+        // sharded: every rank makes all Ng draws and keeps those in its own weight range
+        const int gs = stride_grid((c.Ng + 1) / 2);
+        APS_LAUNCH(2, k_multi_search<1><<<gs, APS_K1_THREADS, 0, st>>>(a, &h->d_sp->key));
+        APS_LAUNCH(2, k_tile_counts<<<gt, APS_THREADS, 0, st>>>(a));
+        APS_LAUNCH(2, k_scan_tile_counts<<<1, APS_THREADS, 0, st>>>(a, nullptr, c, t));
+        APS_LAUNCH(2, k_expand_counts<<<gt, APS_THREADS, 0, st>>>(a, anc_slab_of(c, t), 1, c, t));
     }
+    if (c.sampler == APS_PGAS && t >= 2 && t <= c.T - 1) {
+        APS_LAUNCH(3, h->f_pmax<<<gp, APS_K1_THREADS, 0, st>>>(c, t, x_slab_of(c, t - 1), anc_slab_of(c, t - 1), anc_slab_of(c, t)));
+        APS_LAUNCH(3, h->f_psel<<<gt, APS_THREADS, 0, st>>>(c, t, x_slab_of(c, t - 1), anc_slab_of(c, t - 1), anc_slab_of(c, t)));
+    }
+}
+
+static void launch_fill_fat(aps_handle *h, const DevCtx &c, long long s, Launcher &L) {
     // children of fat parents at the final decision point (no propagate kernel follows to resolve them)
     // (sharded: every block spins on the peers first, so the grid stays small -- ranks emulated on one
     // GPU must all fit at once; the fill itself is a few MB at most, once per sweep)
-    APS_LAUNCH(2, k_fill_fat<<<c.world > 1 ? 16 : sm_count() * 2, APS_K1_THREADS, 0, st>>>(c, c.T, anc_slab(c.T), 1));
-#undef APS_LAUNCH
-    return n;
+    APS_LAUNCH(2, k_fill_fat<<<c.world > 1 ? 16 : sm_count() * 2, APS_K1_THREADS, 0, h->stream>>>(c, s, anc_slab_of(c, s), 1));
+}
+
+static void reset_sweep_scratch(aps_handle *h) {
+    const DevCtx &c = h->ctx;
+    cudaStream_t st = h->stream;
+    cudaMemsetAsync(c.acc, 0, sizeof(StepAcc) * (size_t)(c.T + 2), st);
+    cudaMemsetAsync(c.fat_cnt, 0, sizeof(int) * (size_t)c.fat_steps, st);
+    if (h->d_rs) {
+        cudaMemsetAsync(h->d_rs, 0, sizeof(ResidualState) * (size_t)(c.T + 2), st);
+        cudaMemsetAsync(h->d_done2, 0, sizeof(unsigned) * (size_t)(c.T + 2), st);
+    }
+}
+
+// enqueue every kernel of one sweep on the handle's stream; returns the number of launches
+static long long enqueue_sweep(aps_handle *h, LaunchProf *prof = nullptr) {
+    const DevCtx &c = h->ctx;
+    cudaStream_t st = h->stream;
+    Launcher L{prof, 0};
+    reset_sweep_scratch(h);
+    k_init_sweep<<<1, 32, 0, st>>>(c);
+    ++L.n;
+    const int gt = (int)c.num_tiles;
+    for (long long t = 1; t <= c.T; ++t) {
+        launch_propagate(h, c, t, L);
+        APS_LAUNCH(1, k_normalise<IN_LOGW><<<gt, APS_K2_THREADS, 0, st>>>(c, c.logw, t));
+        launch_decision(h, c, t, h->f_res, L);
+    }
+    launch_fill_fat(h, c, c.T, L);
+    return L.n;
 }
 
 static int sweep_impl(aps_handle *h, uint64_t master_seed, const double *ref_traj, double *logevidence,
@@ -596,6 +635,7 @@ static int sweep_impl(aps_handle *h, uint64_t master_seed, const double *ref_tra
         for (cudaEvent_t e : prof.ev) cudaEventDestroy(e);
     }
     h->swept = true;
+    h->pc_active = false;
     if (h->h_st->err)
         return fail(h->h_st->err, h->h_st->err == APS_ERR_COMM
                                       ? "aps_sweep: a peer rank did not answer within the exchange timeout"
@@ -626,6 +666,175 @@ extern "C" int aps_sweep_profiled(aps_handle *h, uint64_t master_seed, const dou
                                   float *class_ms, int64_t *class_launches) {
     if (!class_ms) return fail(APS_ERR_INVALID, "aps_sweep_profiled: null class_ms");
     return sweep_impl(h, master_seed, ref_traj, logevidence, class_ms, class_launches);
+}
+
+// ================================================================== container level (stepwise)
+// The device-resident ParticleContainer driven call by call (include/aps_b200.h). Uses the
+// per-step kernels with the plan written by the normalise kernel (no deferred plan), so that every
+// call leaves the container in a state the accessors can read.
+static DevCtx pc_ctx(aps_handle *h) {
+    DevCtx c = h->ctx;
+    c.defer_plan = 0;
+    return c;
+}
+#define NEED_PC(name)                                                                               \
+    if (!h) return fail(APS_ERR_INVALID, name ": null handle");                                     \
+    if (!h->pc_active) return fail(APS_ERR_INVALID, name ": aps_pc_begin has not been called");     \
+    CU(cudaSetDevice(h->cfg.device));
+
+// max + normalise of the current log-weights into (acc[s], plan[s]); s = T + 1 is scratch
+static int pc_normalise(aps_handle *h, const DevCtx &c, long long s) {
+    CU(cudaMemsetAsync(c.acc + s, 0, sizeof(StepAcc), h->stream));
+    k_vector_max<IN_LOGW><<<stride_grid(c.N), APS_K1_THREADS, 0, h->stream>>>(c.logw, c.N, c.acc + s);
+    k_normalise<IN_LOGW><<<(int)c.num_tiles, APS_K2_THREADS, 0, h->stream>>>(c, c.logw, s);
+    return APS_OK;
+}
+
+static int pc_sync_state(aps_handle *h, const char *what) {
+    CU(cudaMemcpyAsync(h->h_st, h->ctx.st, sizeof(SweepState), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaGetLastError());
+    if (h->h_st->err)
+        return fail(h->h_st->err, std::string(what) + ": particle weights could not be normalised (all -Inf or NaN log-weights)");
+    return APS_OK;
+}
+
+extern "C" int aps_pc_begin(aps_handle *h, uint64_t master_seed, const double *ref_traj) {
+    if (!h) return fail(APS_ERR_INVALID, "aps_pc_begin: null handle");
+    if (!h->has_obs) return fail(APS_ERR_INVALID, "aps_pc_begin: observations not set");
+    if (h->ctx.world > 1) return fail(APS_ERR_INVALID, "aps_pc_begin: the stepwise container is single-GPU only");
+    CU(cudaSetDevice(h->cfg.device));
+    const DevCtx &c = h->ctx;
+    int has_ref = 0;
+    if (ref_traj != nullptr) {
+        if (h->cfg.sampler == APS_SMC) return fail(APS_ERR_INVALID, "aps_pc_begin: SMC takes no reference trajectory");
+        if (c.N < 2) return fail(APS_ERR_INVALID, "aps_pc_begin: a conditional sweep needs at least 2 particles");
+        if (ref_traj == APS_REF_ON_DEVICE) {
+            if (!h->ref_valid) return fail(APS_ERR_INVALID, "aps_pc_begin: no trajectory has been picked yet");
+        } else {
+            CU(cudaMemcpyAsync(h->d_ref, ref_traj, sizeof(double) * (size_t)c.T * c.d, cudaMemcpyHostToDevice, h->stream));
+            h->ref_valid = true;
+        }
+        has_ref = 1;
+    }
+    h->h_sp->key = master_seed;
+    h->h_sp->has_ref = has_ref;
+    h->h_sp->pad = 0;
+    h->h_sp->epoch = h->epoch++;
+    CU(cudaMemcpyAsync(h->d_sp, h->h_sp, sizeof(SweepParams), cudaMemcpyHostToDevice, h->stream));
+    reset_sweep_scratch(h);
+    CU(cudaMemsetAsync(c.logw, 0, sizeof(double) * (size_t)c.NS, h->stream));
+    k_init_sweep<<<1, 32, 0, h->stream>>>(c);
+    // decision point 0 is provisional until resample_propagate! runs on it
+    k_pc_provisional<<<1, APS_K1_THREADS, 0, h->stream>>>(c, 0, anc_slab_of(c, 0));
+    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaGetLastError());
+    h->pc_active = true;
+    h->pc_t = 0;
+    h->pc_decided = 0;
+    h->swept = false;
+    return APS_OK;
+}
+
+extern "C" int aps_pc_reweight(aps_handle *h, int32_t *isdone_out) {
+    NEED_PC("aps_pc_reweight");
+    const DevCtx c = pc_ctx(h);
+    if (h->pc_t >= c.T) {  // every particle is done (src/container.jl:288): nothing changes
+        if (isdone_out) *isdone_out = 1;
+        return APS_OK;
+    }
+    const long long t = ++h->pc_t;
+    Launcher L{nullptr, 0};
+    launch_propagate(h, c, t, L);
+    // provisional decision point t: plan (logZ, ESS, ...) of the new weights, identity ancestors,
+    // weights kept -- until aps_pc_resample_propagate settles it
+    int rc = pc_normalise(h, c, t);
+    if (rc) return rc;
+    k_pc_provisional<<<stride_grid(c.N), APS_K1_THREADS, 0, h->stream>>>(c, t, anc_slab_of(c, t));
+    if (isdone_out) *isdone_out = 0;
+    h->swept = h->pc_t == c.T;
+    // a weight vector that cannot be normalised is reported by the call that needs it normalised
+    // (resample_propagate! / logZ), like upstream
+    CU(cudaMemsetAsync(&h->ctx.st->err, 0, sizeof(int), h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaGetLastError());
+    return APS_OK;
+}
+
+extern "C" int aps_pc_resample_propagate(aps_handle *h, int32_t *resampled_out) {
+    NEED_PC("aps_pc_resample_propagate");
+    const DevCtx c = pc_ctx(h);
+    const long long s = h->pc_t;
+    int resampled = 0;
+    if (s == 0) {
+        // particles carry no state yet: resampling them only re-keys (src/container.jl:325 at c = 1);
+        // with position-derived counters that is the identity. The decision is the one k_init_sweep made.
+        StepPlan p;
+        k_init_sweep<<<1, 32, 0, h->stream>>>(c);
+        CU(cudaMemcpyAsync(&p, c.plan, sizeof(StepPlan), cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        resampled = p.resampled;
+    } else {
+        CU(cudaMemsetAsync(c.fat_cnt + s, 0, sizeof(int), h->stream));
+        if (h->d_rs) {
+            CU(cudaMemsetAsync(h->d_rs + s, 0, sizeof(ResidualState), h->stream));
+            CU(cudaMemsetAsync(h->d_done2 + s, 0, sizeof(unsigned), h->stream));
+        }
+        int rc = pc_normalise(h, c, s);
+        if (rc) return rc;
+        Launcher L{nullptr, 0};
+        launch_decision(h, c, s, pick_resample(c.resampler, false, false), L);
+        k_fill_fat<<<sm_count() * 2, APS_K1_THREADS, 0, h->stream>>>(c, s, anc_slab_of(c, s), 0);
+        StepPlan p;
+        CU(cudaMemcpyAsync(&p, c.plan + s, sizeof(StepPlan), cudaMemcpyDeviceToHost, h->stream));
+        rc = pc_sync_state(h, "aps_pc_resample_propagate");
+        if (rc) return rc;
+        resampled = p.resampled;
+        if (resampled) CU(cudaMemsetAsync(c.logw, 0, sizeof(double) * (size_t)c.NS, h->stream));  // reset_logweights!, :228
+        CU(cudaStreamSynchronize(h->stream));
+    }
+    h->pc_decided = s + 1;
+    if (resampled_out) *resampled_out = resampled;
+    return APS_OK;
+}
+
+extern "C" int aps_pc_logz(aps_handle *h, double *logz_out) {
+    NEED_PC("aps_pc_logz");
+    if (!logz_out) return fail(APS_ERR_INVALID, "aps_pc_logz: null output");
+    const DevCtx c = pc_ctx(h);
+    int rc = pc_normalise(h, c, c.T + 1);
+    if (rc) return rc;
+    StepPlan p;
+    CU(cudaMemcpyAsync(&p, c.plan + c.T + 1, sizeof(StepPlan), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemsetAsync(&h->ctx.st->err, 0, sizeof(int), h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaGetLastError());
+    if (p.err) {
+        if (p.M == -INFINITY) {  // logsumexp of all -Inf is -Inf, not an error
+            *logz_out = -INFINITY;
+            return APS_OK;
+        }
+        return fail(APS_ERR_WEIGHTS, "aps_pc_logz: NaN or +Inf log-weight");
+    }
+    *logz_out = p.logZ;
+    return APS_OK;
+}
+
+extern "C" int aps_set_logweights(aps_handle *h, const double *logw) {
+    NEED_PC("aps_set_logweights");
+    if (!logw) return fail(APS_ERR_INVALID, "aps_set_logweights: null argument");
+    if (h->pc_t == 0) return fail(APS_ERR_INVALID, "aps_set_logweights: call it after the first aps_pc_reweight");
+    const DevCtx c = pc_ctx(h);
+    CU(cudaMemcpyAsync(c.logw, logw, sizeof(double) * (size_t)c.N, cudaMemcpyHostToDevice, h->stream));
+    // keep the provisional plan of the current decision point in step with the new weights
+    int rc = pc_normalise(h, c, h->pc_t);
+    if (rc) return rc;
+    k_pc_provisional<<<stride_grid(c.N), APS_K1_THREADS, 0, h->stream>>>(c, h->pc_t, anc_slab_of(c, h->pc_t));
+    CU(cudaMemsetAsync(&h->ctx.st->err, 0, sizeof(int), h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaGetLastError());
+    h->pc_decided = h->pc_t;  // the decision point is open again
+    return APS_OK;
 }
 
 #define NEED_SWEEP(name)                                                        \
@@ -686,6 +895,13 @@ extern "C" int aps_get_weights_view(aps_handle *h, const double **w_out) {
 }
 
 extern "C" int aps_get_logweights(aps_handle *h, double *logw_out) {
+    if (h && h->pc_active) {  // stepwise container: pc.logWs as it stands (reset_logweights! zeroes the buffer there)
+        if (!logw_out) return fail(APS_ERR_INVALID, "aps_get_logweights: null output");
+        CU(cudaSetDevice(h->cfg.device));
+        CU(cudaMemcpyAsync(logw_out, h->ctx.logw, sizeof(double) * (size_t)h->ctx.N, cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        return APS_OK;
+    }
     NEED_SWEEP("aps_get_logweights");
     if (!logw_out) return fail(APS_ERR_INVALID, "aps_get_logweights: null output");
     int res = 0;
@@ -722,6 +938,50 @@ extern "C" int aps_get_trajectory(aps_handle *h, int64_t slot, double *traj_out)
     CU(cudaStreamSynchronize(h->stream));
     CU(cudaGetLastError());
     return APS_OK;
+}
+
+extern "C" int aps_get_trajectories(aps_handle *h, double *traj_out) {
+    NEED_SWEEP("aps_get_trajectories");
+    if (!traj_out) return fail(APS_ERR_INVALID, "aps_get_trajectories: null output");
+    if (!h->cfg.keep_history) return fail(APS_ERR_INVALID, "aps_get_trajectories: handle was created with keep_history = 0");
+    const DevCtx &c = h->ctx;
+    int32_t *d_idx = nullptr;
+    double *d_out[2] = {nullptr, nullptr};  // double-buffered: the copy of step t overlaps the gather of step t-1
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    CU(cudaMalloc(&d_idx, sizeof(int32_t) * (size_t)c.N));
+    const size_t step_bytes = sizeof(double) * (size_t)c.N * c.d;
+    int rc = APS_OK;
+    for (int b = 0; b < 2 && rc == APS_OK; ++b) {
+        if (cudaMalloc(&d_out[b], step_bytes) != cudaSuccess || cudaEventCreate(&ev[b]) != cudaSuccess)
+            rc = fail(APS_ERR_NOMEM, "aps_get_trajectories: scratch allocation failed");
+    }
+    cudaStream_t cp = nullptr;
+    if (rc == APS_OK && cudaStreamCreateWithFlags(&cp, cudaStreamNonBlocking) != cudaSuccess)
+        rc = fail(APS_ERR_CUDA, "aps_get_trajectories: stream creation failed");
+    if (rc == APS_OK) {
+        cudaEvent_t done_k;
+        cudaEventCreate(&done_k);
+        for (long long t = c.T; t >= 1; --t) {
+            const int b = (int)(t & 1);
+            cudaStreamWaitEvent(h->stream, ev[b], 0);  // the copy that last used this buffer is complete
+            k_traj_step<<<stride_grid(c.N), APS_K1_THREADS, 0, h->stream>>>(c, t, d_idx, d_out[b]);
+            cudaEventRecord(done_k, h->stream);
+            cudaStreamWaitEvent(cp, done_k, 0);
+            cudaMemcpyAsync(traj_out + (size_t)(t - 1) * c.N * c.d, d_out[b], step_bytes, cudaMemcpyDeviceToHost, cp);
+            cudaEventRecord(ev[b], cp);
+        }
+        cudaStreamSynchronize(h->stream);
+        cudaStreamSynchronize(cp);
+        cudaEventDestroy(done_k);
+        if (cudaGetLastError() != cudaSuccess) rc = fail(APS_ERR_CUDA, "aps_get_trajectories: kernel or copy failed");
+    }
+    if (cp) cudaStreamDestroy(cp);
+    for (int b = 0; b < 2; ++b) {
+        if (ev[b]) cudaEventDestroy(ev[b]);
+        cudaFree(d_out[b]);
+    }
+    cudaFree(d_idx);
+    return rc;
 }
 
 extern "C" int aps_get_step_stats(aps_handle *h, double *logz_out, double *ess_out, uint8_t *resampled_out) {

@@ -93,7 +93,9 @@ __device__ __forceinline__ int fat_lookup(const FatEntry *ent, int nfat, int g) 
     int a = -1;
 #pragma unroll 1
     for (int e = 0; e < nfat; ++e) {
-        const int4 v = __ldg(reinterpret_cast<const int4 *>(ent + e));
+        // (not __ldg: sharded, peers may still be pushing into later lists while this kernel runs, which
+        // breaks the read-only contract of ld.global.nc; L2 is the coherence point for peer writes)
+        const int4 v = __ldcg(reinterpret_cast<const int4 *>(ent + e));
         if (g >= v.x && g < v.y) a = v.z;
     }
     return a;
@@ -108,22 +110,30 @@ __device__ __forceinline__ void st_sys_u64(u64 *p, u64 v) {
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
-// Exchanges are push + poll with no system-scope fences. Scalars that a kernel reduces (the
-// log-weight maximum, the integer totals) are pushed to every rank's mailbox by the LAST block of
-// the producing kernel (device-scope ticket), so they travel over NVLink while the kernel drains
-// and the next one launches. The barrier after the ancestor scatter is different: the peer stores
-// of all blocks must have landed, which holds when the NEXT kernel of the stream starts, so block
-// 0 of the consumer kernel posts it. In both cases all blocks of the consumer kernel, on every
-// rank, spin on their LOCAL mailbox until every rank's values for the expected sequence number
-// are there.
-// Each value travels with its sequence number in one 16-byte store (one NVLink transaction), so
-// no ordering between separate stores is needed.
+// Exchanges are push + poll. Scalars that a kernel reduces (the log-weight maximum, the integer
+// totals) are pushed to every rank's mailbox by the LAST block of the producing kernel
+// (device-scope ticket), so they travel over NVLink while the kernel drains and the next one
+// launches. The barrier after the ancestor scatter is different: the peer stores of all blocks
+// must have landed, which holds when the NEXT kernel of the stream starts, so block 0 of the
+// consumer kernel posts it. In both cases all blocks of the consumer kernel, on every rank, spin on
+// their LOCAL mailbox until every rank's values for the expected sequence number are there.
+//
+// Memory model. A value travels with its sequence number in ONE 128-bit access (st / ld .b128:
+// single-copy atomic), the post is a RELEASE at system scope (everything the posting thread
+// observed before it -- its block's and, across the kernel boundary, the previous kernel's peer
+// stores -- is visible to whoever acquires the pair) and the successful poll is an ACQUIRE; the
+// __syncthreads() that follows every wait extends the edge to the rest of the consumer block. The
+// data path itself (ancestor scatter, state gathers, fat-list entries) stays plain / relaxed.
 __device__ __forceinline__ void st_pair_sys(ulonglong2 *p, u64 v, u64 seq) {
-    asm volatile("st.relaxed.sys.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(v), "l"(seq) : "memory");
+    asm volatile("{ .reg .b128 t; mov.b128 t, {%1, %2}; st.release.sys.global.b128 [%0], t; }" ::"l"(p), "l"(v), "l"(seq)
+                 : "memory");
 }
 __device__ __forceinline__ ulonglong2 ld_pair_sys(const ulonglong2 *p) {
     ulonglong2 r;
-    asm volatile("ld.relaxed.sys.global.v2.u64 {%0, %1}, [%2];" : "=l"(r.x), "=l"(r.y) : "l"(p) : "memory");
+    asm volatile("{ .reg .b128 t; ld.acquire.sys.global.b128 t, [%2]; mov.b128 {%0, %1}, t; }"
+                 : "=l"(r.x), "=l"(r.y)
+                 : "l"(p)
+                 : "memory");
     return r;
 }
 // publish nv values of this rank (threads 0..world-1 of ONE block; thread r writes to rank r)
@@ -135,21 +145,31 @@ __device__ __forceinline__ void mail_post(const PeerTable *pt, int rank, int wor
         for (int k = 0; k < nv; ++k) st_pair_sys(&dst->pair[k], v[k], seq);
     }
 }
+// Spin budget of one wait, in SM cycles (~2 GHz): APS_COMM_TIMEOUT_MS, default 3000 ms. A dead peer
+// costs ONE such timeout per sweep: the first wait that expires raises the sweep's error flag and
+// every later wait gives up as soon as it sees the flag.
+__device__ long long g_spin_limit = 6000000000LL;
 // wait for every rank's nv values of sequence number `seq` (threads 0..world-1 of a block; thread
-// r reads slot r of the local mailbox into out[r]). Returns false on timeout (~3 s: a peer is gone).
+// r reads slot r of the local mailbox into out[r]). Returns false on timeout (a peer is gone) or
+// when *errflag is already set.
 __device__ __forceinline__ bool mail_wait(const PeerTable *pt, int rank, int world, int kind, u64 seq, u64 (*out)[4],
-                                          int nv, unsigned long long *spin = nullptr) {
+                                          int nv, unsigned long long *spin = nullptr, const int *errflag = nullptr,
+                                          int limit_mul = 1) {
     const int r = threadIdx.x;
     bool ok = true;
     if (r < world) {
         const MailSlot *src = pt->mail[rank] + kind * APS_MAX_RANKS + r;
         const long long t0 = clock64();
+        const long long limit = g_spin_limit * limit_mul;
         for (int k = 0; k < nv; ++k) {
             ulonglong2 pr = ld_pair_sys(&src->pair[k]);
+            unsigned it = 0;
             while (pr.y < seq) {
-                if (clock64() - t0 > 6000000000LL) {
-                    ok = false;
-                    break;
+                if ((++it & 63u) == 0) {
+                    if (clock64() - t0 > limit || (errflag && *reinterpret_cast<const volatile int *>(errflag) == APS_ERR_COMM)) {
+                        ok = false;
+                        break;
+                    }
                 }
                 pr = ld_pair_sys(&src->pair[k]);
             }

@@ -154,7 +154,7 @@ __global__ void APS_K1_BOUNDS k_propagate(const __grid_constant__ DevCtx c, cons
         __shared__ u64 s_w[APS_MAX_RANKS][4];
         const u64 v0 = 0;
         if (blockIdx.x == 0) mail_post(c.peers, c.rank, c.world, 2, seq0 + (u64)(t - 1) + 1, &v0, 1);
-        if (!(c.dbg & 1) && !mail_wait(c.peers, c.rank, c.world, 2, seq0 + (u64)(t - 1) + 1, s_w, 1, c.st->spin))
+        if (!(c.dbg & 1) && !mail_wait(c.peers, c.rank, c.world, 2, seq0 + (u64)(t - 1) + 1, s_w, 1, c.st->spin, &c.st->err, t == 1 ? 20 : 1))
             c.st->err = APS_ERR_COMM;
         __syncthreads();
         resolve_fat();  // the peers' pushes into this rank's list are complete now
@@ -380,7 +380,7 @@ __global__ void __launch_bounds__(APS_K2_THREADS) k_normalise(const __grid_const
         if (threadIdx.x == 0) s_okm = 1;
         __syncthreads();
         // (published by the last block of every rank's propagate kernel)
-        if (!(c.dbg & 1) && !mail_wait(c.peers, c.rank, c.world, 0, seq, s_m, 2, c.st ? c.st->spin : nullptr)) s_okm = 0;
+        if (!(c.dbg & 1) && !mail_wait(c.peers, c.rank, c.world, 0, seq, s_m, 2, c.st ? c.st->spin : nullptr, c.st ? &c.st->err : nullptr)) s_okm = 0;
         if (c.dbg & 1) { if (threadIdx.x < c.world) { s_m[threadIdx.x][0] = acc->max_enc; s_m[threadIdx.x][1] = 0; } }
         __syncthreads();
         max_enc = 0;
@@ -497,7 +497,7 @@ __device__ __forceinline__ bool block_exchange(const DevCtx &c, int kind, u64 se
     __syncthreads();
     mail_post(c.peers, c.rank, c.world, kind, seq, v, nv);
     bool ok = true;
-    if (!(c.dbg & 1)) ok = mail_wait(c.peers, c.rank, c.world, kind, seq, out, nv, c.st ? c.st->spin : nullptr);
+    if (!(c.dbg & 1)) ok = mail_wait(c.peers, c.rank, c.world, kind, seq, out, nv, c.st ? c.st->spin : nullptr, c.st ? &c.st->err : nullptr);
     return __syncthreads_and(ok ? 1 : 0) != 0;
 }
 __device__ __forceinline__ u64 step_seq(const DevCtx &c, long long s) { return c.sp->epoch * (u64)(c.T + 2) + (u64)s + 1; }
@@ -527,7 +527,7 @@ __device__ __forceinline__ void multi_plan(const DevCtx &c, long long s, const u
 __global__ void __launch_bounds__(32) k_plan_multi(const __grid_constant__ DevCtx c, const long long s) {
     __shared__ u64 s_t[APS_MAX_RANKS][4];
     bool ok = true;  // the totals were published by the last block of every rank's normalise kernel
-    if (!(c.dbg & 1)) ok = mail_wait(c.peers, c.rank, c.world, 1, step_seq(c, s), s_t, 4, c.st->spin);
+    if (!(c.dbg & 1)) ok = mail_wait(c.peers, c.rank, c.world, 1, step_seq(c, s), s_t, 4, c.st->spin, &c.st->err);
     ok = __syncthreads_and(ok ? 1 : 0) != 0;
     if (threadIdx.x == 0) {
         StepPlan p;
@@ -1005,7 +1005,7 @@ __global__ void __launch_bounds__(APS_K3_THREADS, MULTI ? APS_K3_MINBLOCKS - 2 :
         __shared__ int s_okt;
         if (tid == 0) s_okt = 1;
         __syncthreads();
-        if (!(c.dbg & 1) && !mail_wait(c.peers, c.rank, c.world, 1, step_seq(c, s), s_t, 4, c.st->spin)) s_okt = 0;
+        if (!(c.dbg & 1) && !mail_wait(c.peers, c.rank, c.world, 1, step_seq(c, s), s_t, 4, c.st->spin, &c.st->err)) s_okt = 0;
         if (c.dbg & 1) { if (tid < c.world) { s_t[tid][0] = 1ull << 50; s_t[tid][1] = 1ull << 30; s_t[tid][2] = 1ull << 40; s_t[tid][3] = c.acc[s].max_enc; } }
         __syncthreads();
         if (tid == 0 || tid == 32) {  // the two halves of the plan on two warps (same arithmetic as multi_plan)
@@ -1566,7 +1566,7 @@ __global__ void __launch_bounds__(APS_THREADS) k_pgas_select(const __grid_consta
         __syncthreads();
         if (blockIdx.x == 0) mail_post(c.peers, c.rank, c.world, 6, step_seq(c, s), s_v, 2);
         bool ok = true;
-        if (!(c.dbg & 1)) ok = mail_wait(c.peers, c.rank, c.world, 6, step_seq(c, s), s_m, 2, nullptr);
+        if (!(c.dbg & 1)) ok = mail_wait(c.peers, c.rank, c.world, 6, step_seq(c, s), s_m, 2, nullptr, &c.st->err);
         if (!__syncthreads_and(ok ? 1 : 0) && threadIdx.x == 0) c.st->err = APS_ERR_COMM;
         menc = 0;
         for (int r = 0; r < c.world; ++r) {
@@ -1814,6 +1814,30 @@ __global__ void __launch_bounds__(APS_K1_THREADS) k_smooth_step(const __grid_con
     }
 }
 
+// One backward step of "all N trajectories" (SMCSample(collect(pc), ...), src/smc.jl:56): out[i][k] =
+// x_t[b_t(i)][k] for this rank's final-set slots i; idx carries b_t(i) -> b_{t-1}(i) like k_smooth_step.
+__global__ void __launch_bounds__(APS_K1_THREADS) k_traj_step(const __grid_constant__ DevCtx c, const long long t,
+                                                           int32_t *__restrict__ idx, double *__restrict__ out) {
+    const long long N = c.N, T = c.T;
+    const int D = c.d;
+    for (long long i = (long long)blockIdx.x * APS_K1_THREADS + threadIdx.x; i < N;
+         i += (long long)gridDim.x * APS_K1_THREADS) {
+        const long long b = t == T ? (long long)c.anc[(T % c.anc_slabs) * c.NS + i] : (long long)idx[i];
+        for (int k = 0; k < D; ++k) out[i * D + k] = load_state(c, (t - 1) % c.x_slabs, k, b);
+        idx[i] = t > 1 ? (int32_t)load_anc(c, (t - 1) % c.anc_slabs, b) : 0;
+    }
+}
+
+// Stepwise container (aps_pc_*): decision point s before resample_propagate! has run on it -- every
+// particle continues as itself and the weights are kept (what update_keys! leaves, container.jl:247)
+__global__ void __launch_bounds__(APS_K1_THREADS) k_pc_provisional(const __grid_constant__ DevCtx c, const long long s,
+                                                                int32_t *__restrict__ anc_out) {
+    for (long long i = (long long)blockIdx.x * APS_K1_THREADS + threadIdx.x; i < c.N;
+         i += (long long)gridDim.x * APS_K1_THREADS)
+        anc_out[i] = (int32_t)(c.slot0 + i);
+    if (blockIdx.x == 0 && threadIdx.x == 0) c.plan[s].resampled = 0;
+}
+
 // normalised weights W_i = q_i / Q (getweights, src/container.jl:95) or 1/N after a resample
 __global__ void __launch_bounds__(APS_THREADS) k_weights_out(const u64 *__restrict__ q, const StepPlan *p, long long N,
                                                              long long Ng, int S, int force_uniform,
@@ -1846,7 +1870,7 @@ __global__ void __launch_bounds__(APS_K1_THREADS) k_fill_fat(const __grid_consta
         const u64 v0 = 0;
         const u64 seq = c.sp->epoch * (u64)(c.T + 2) + (u64)s + 1;
         if (blockIdx.x == 0) mail_post(c.peers, c.rank, c.world, 2, seq, &v0, 1);
-        if (!(c.dbg & 1) && !mail_wait(c.peers, c.rank, c.world, 2, seq, s_w, 1, nullptr)) c.st->err = APS_ERR_COMM;
+        if (!(c.dbg & 1) && !mail_wait(c.peers, c.rank, c.world, 2, seq, s_w, 1, nullptr, &c.st->err)) c.st->err = APS_ERR_COMM;
         __syncthreads();
     }
     int nfat = c.fat_cnt[s];

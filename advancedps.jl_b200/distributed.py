@@ -94,7 +94,7 @@ def sample(rng, model, sampler, n_iter=None, group=None):
     if isinstance(sampler, S.SMC):
         h = _sharded_handle(model, sampler, group)
         logev = h.sweep(_shared_key(rng, group))
-        return S.SMCSample(h, model, h.weights_view(), logev)
+        return S.SMCSample(h, model, h.weights(), logev)
     if n_iter is None:
         raise TypeError("sample(rng, model, PG|PGAS, n_iter): n_iter is required")
     out, state = [], None
@@ -113,7 +113,7 @@ def step(rng, model, sampler, state=None, group=None):
     key = _shared_key(rng, group)
     if state is None:
         logev = h.sweep(key)
-    elif state._handle is h:
+    elif state._on_device(h):
         logev = h.sweep(key, ref_on_device=True)
     else:
         logev = h.sweep(key, ref_traj=state.trajectory.model.X)

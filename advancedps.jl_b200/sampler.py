@@ -146,23 +146,46 @@ class Trace:
 
 
 class SMCSample:
-    """SMCSample(trajectories, weights, logevidence) (src/smc.jl:23-27); trajectories are
-    materialised lazily through the device genealogy."""
+    """SMCSample(trajectories, weights, logevidence) (src/smc.jl:23-27). ``weights`` and
+    ``logevidence`` are owned values, like upstream's. ``trajectories`` is materialised through
+    the device genealogy on access: one at a time (``smp.trajectories[i]``) or all at once
+    (``smp.trajectories.materialize()``, T x N x d). The genealogy lives in the device store that
+    the next ``sample`` / ``step`` on the same model overwrites; access after that raises instead
+    of returning another sweep's particles (``sample(..., materialize=True)`` copies up front)."""
 
-    def __init__(self, handle, tssm, weights, logevidence):
+    def __init__(self, handle, tssm, weights, logevidence, materialize=False):
         self._h, self._tssm = handle, tssm
         self.weights = weights
         self.logevidence = logevidence
         self.trajectories = _LazyTrajectories(handle, tssm)
+        if materialize:
+            self.trajectories.materialize()
 
     def smoothed_mean(self):
         """Weighted mean trajectory sum_i W_i X_i (T x d), computed on the device from the genealogy."""
+        self.trajectories._check_fresh()
         return self._h.smoothing_mean()
 
 
 class _LazyTrajectories:
     def __init__(self, handle, tssm):
         self._h, self._tssm = handle, tssm
+        self._gen = handle.generation
+        self._all = None
+
+    def _check_fresh(self):
+        if self._h.generation != self._gen:
+            raise ApsError(_abi.ERR_INVALID,
+                           "this SMCSample's trajectories were not materialised before a later sample()/step() "
+                           "reused the device particle store; call .trajectories.materialize() (or pass "
+                           "materialize=True to sample) before the next call on the same model")
+
+    def materialize(self):
+        """Copy all N trajectories to the host (T x N x d) and serve every later access from there."""
+        if self._all is None:
+            self._check_fresh()
+            self._all = self._h.trajectories()
+        return self._all
 
     def __len__(self):
         return self._h.N
@@ -170,9 +193,17 @@ class _LazyTrajectories:
     def __getitem__(self, i):
         if not 0 <= i < self._h.N:
             raise IndexError(i)
-        return Trace(TracedSSM(self._tssm.model, self._tssm.Y, self._h.trajectory(i)))
+        if self._all is not None:
+            X = self._all[:, i, :].copy()
+        else:
+            self._check_fresh()
+            X = self._h.trajectory(i)
+        return Trace(TracedSSM(self._tssm.model, self._tssm.Y, X))
 
     def final_states(self):
+        if self._all is not None:
+            return self._all[-1].copy()
+        self._check_fresh()
         return self._h.final_states()
 
 
@@ -181,7 +212,13 @@ class PGState:
 
     def __init__(self, trajectory, handle=None):
         self.trajectory = trajectory
-        self._handle = handle  # lets the next step condition on the device-resident copy
+        # lets the next step condition on the device-resident copy -- as long as that copy is still
+        # this state's trajectory (another chain on the same model may have replaced it)
+        self._handle = handle
+        self._ref_token = handle.ref_token if handle is not None else None
+
+    def _on_device(self, h):
+        return self._handle is h and self._ref_token == h.ref_token
 
 
 class PGSample:
@@ -214,7 +251,7 @@ def _handle_for(tssm, sampler, keep_history=True):
     return h
 
 
-def sample(rng, model, sampler, n_iter=None, **kwargs):
+def sample(rng, model, sampler, n_iter=None, materialize=False, **kwargs):
     """AbstractMCMC.sample. ``SMC`` -> SMCSample (src/smc.jl:35-57); ``PG``/``PGAS`` with
     ``n_iter`` -> list of PGSample (AbstractMCMC's loop around ``step``)."""
     if isinstance(sampler, SMC):
@@ -222,9 +259,8 @@ def sample(rng, model, sampler, n_iter=None, **kwargs):
             warnings.warn(f"keyword arguments {tuple(kwargs)} are not supported by `SMC`")  # smc.jl:41-43
         h = _handle_for(model, sampler)
         logev = h.sweep(_draw_key(rng))
-        # weights: a view of the handle's pinned host buffer (valid until the next call on this
-        # model's handle; copy it to keep it) -- the D2H copy runs at DMA speed, no staging pass
-        return SMCSample(h, model, h.weights_view(), logev)
+        # weights: an owned copy, as upstream returns (src/smc.jl:56)
+        return SMCSample(h, model, h.weights(), logev, materialize=materialize)
     if n_iter is None:
         raise TypeError("sample(rng, model, PG|PGAS, n_iter): n_iter is required")
     out, state = [], None
@@ -241,7 +277,7 @@ def step(rng, model, sampler, state=None, **kwargs):
     h = _handle_for(model, sampler)
     if state is None:
         logev = h.sweep(_draw_key(rng))
-    elif state._handle is h:
+    elif state._on_device(h):
         logev = h.sweep(_draw_key(rng), ref_on_device=True)
     else:
         logev = h.sweep(_draw_key(rng), ref_traj=state.trajectory.model.X)
@@ -368,3 +404,60 @@ def sweep_(rng, pc, resampler, sampler, ref=None):
         logZ1 = logZ(pc)
         logevidence += logZ1 - logZ0
     return logevidence
+
+
+# ------------------------------------------------------------------ device-resident container
+class DeviceParticleContainer:
+    """The ParticleContainer of a recognised state-space family, resident on the GPU and driven call
+    by call like the reference's own tests drive theirs (test/container.jl:28-119,
+    test/pgas.jl:61-91): ``reweight_``, ``resample_propagate_``, ``logZ``, assignable ``logWs``.
+    ``sweep_`` below is the loop of src/container.jl:316-363 over these calls; ``sample`` / ``step``
+    run the same sweep fused on the device (``aps_sweep``)."""
+
+    def __init__(self, model, sampler, rng=None, ref_traj=None):
+        self.model, self.sampler = model, sampler
+        self._h = _handle_for(model, sampler)
+        self._h.pc_begin(_draw_key(rng), ref_traj=ref_traj)
+        self.ref = ref_traj
+
+    def __len__(self):
+        return self._h.N
+
+    @property
+    def logWs(self):
+        return self._h.logweights()
+
+    @logWs.setter
+    def logWs(self, v):  # pc.logWs = [...] (test/pgas.jl:82)
+        self._h.set_logweights(v)
+
+    def reweight_(self):
+        return self._h.pc_reweight()
+
+    def resample_propagate_(self):
+        return self._h.pc_resample_propagate()
+
+    def logZ(self):
+        return self._h.pc_logZ()
+
+    def getweights(self):
+        return self._h.weights()
+
+    def trajectory(self, i):
+        """X of particle ``i`` (0-based) of the current set: ``pc.vals[i+1].model.X`` upstream."""
+        return self._h.trajectory(i)
+
+    def sweep_(self):
+        """sweep! (src/container.jl:316-363) call by call; same result as ``aps_sweep``."""
+        self.resample_propagate_()
+        logZ0 = self.logZ()
+        isdone = self.reweight_()
+        logZ1 = self.logZ()
+        logevidence = logZ1 - logZ0
+        while not isdone:
+            self.resample_propagate_()
+            logZ0 = self.logZ()
+            isdone = self.reweight_()
+            logZ1 = self.logZ()
+            logevidence += logZ1 - logZ0
+        return logevidence

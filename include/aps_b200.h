@@ -107,6 +107,10 @@ int aps_get_final_states(aps_handle *h, double *x_out /* N x d */);        /* co
 int aps_get_trajectory(aps_handle *h, int64_t slot, double *traj_out /* T x d */);
 int aps_get_step_stats(aps_handle *h, double *logz_out /* T */, double *ess_out /* T+1 */,
                        uint8_t *resampled_out /* T+1 */);
+/* every trajectory of the final particle set at once: traj_out[t-1][i][k], T x N x d host doubles
+ * -- what SMCSample(collect(pc), ...) holds (src/smc.jl:56). One backward pass over the ancestor
+ * store on the device, one N x d copy per time step (sharded: this rank's slots).               */
+int aps_get_trajectories(aps_handle *h, double *traj_out /* T x N x d */);
 /* genealogy slabs, for parity tests: states of time t (1..T) as N x d; ancestors used to
  * build time t (2..T+1; T+1 = final resampled set) as N int32, 0-based.                         */
 int aps_get_states(aps_handle *h, int64_t t, double *x_out);
@@ -124,6 +128,30 @@ int aps_get_fat_counts(aps_handle *h, int32_t *counts_out /* T+1 */);
 int aps_last_sweep_ms(aps_handle *h, float *ms_out);
 /* kernels launched by the last aps_sweep (nodes of the replayed CUDA graph count one each)     */
 int aps_last_sweep_launches(aps_handle *h, int64_t *n_out);
+
+/* ---- container level (boundary 2/3): the device-resident ParticleContainer driven
+ *      call by call, the way the reference's own tests drive theirs (test/container.jl:28-119,
+ *      test/pgas.jl:61-91): sweep! is the loop
+ *          resample_propagate! -> logZ0 -> reweight! -> logZ1 -> logevidence += logZ1 - logZ0
+ *      (src/container.jl:316-363) and each piece is callable. Single-GPU handles only.
+ *
+ * aps_pc_begin             ParticleContainer(particles, TracedRNG(), rng) + seed_from_rng!
+ *                          (src/container.jl:22-27,143-159): N fresh particles, logWs = 0, step
+ *                          counter 0; ref_traj as in aps_sweep.
+ * aps_pc_resample_propagate resample_propagate!(rng, pc, sampler, resampler, ref) with the handle's
+ *                          resampler / ESS threshold (src/container.jl:171-251), incl. update_ref!
+ *                          for PGAS (src/pgas.jl:113-128); *resampled_out = 1 if it resampled.
+ * aps_pc_reweight          reweight!(pc, ref) (src/container.jl:259-302): every particle advances
+ *                          one step and adds its score; *isdone_out = 1 (and nothing changes) when
+ *                          all particles had already consumed their T observations.
+ * aps_pc_logz              logZ(pc) (src/container.jl:109).
+ * aps_set_logweights       pc.logWs = v (a mutable field upstream; test/pgas.jl:82 assigns it).
+ * After the loop every accessor above (aps_get_*, aps_pick_trajectory) works as after aps_sweep. */
+int aps_pc_begin(aps_handle *h, uint64_t master_seed, const double *ref_traj);
+int aps_pc_resample_propagate(aps_handle *h, int32_t *resampled_out);
+int aps_pc_reweight(aps_handle *h, int32_t *isdone_out);
+int aps_pc_logz(aps_handle *h, double *logz_out);
+int aps_set_logweights(aps_handle *h, const double *logw /* N */);
 
 /* ---- operator level (boundary 1): the resampler callable
  *      (rng, w, n) -> Vector{Int} used at src/container.jl:182, and the weight helpers of

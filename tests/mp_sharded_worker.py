@@ -52,6 +52,26 @@ def main():
         h.close()
         checked += 1
 
+    # ---- configs[4] at its own T = 100: the resampler sweep, every field against the unsharded oracle
+    T5 = 100
+    _, Y5 = O.simulate_data(m, T5, 0xDA7A0005)
+    for res in (_abi.RESAMPLE_SYSTEMATIC, _abi.RESAMPLE_STRATIFIED, _abi.RESAMPLE_RESIDUAL, _abi.RESAMPLE_MULTINOMIAL):
+        h = D.create_sharded_handle(m, N, T5, Y5, resampler=res, device=local)
+        le = h.sweep(4321)
+        ro = O.sweep(_abi.make_config(m, N, T5, resampler=res), Y5, 4321, mode=O.CANON)
+        lo, hi = D.shard_bounds(N, world, rank)
+        assert le == ro.logevidence, ("c5", res, le, ro.logevidence)
+        logz, ess, rs = h.step_stats()
+        assert np.array_equal(logz, ro.logz) and np.array_equal(ess, ro.ess) and np.array_equal(rs, ro.resampled)
+        for t in range(1, T5 + 1):
+            assert np.array_equal(h.states(t), ro.x_hist[t - 1][lo:hi]), f"c5 res {res}: states differ at t={t}"
+        for t in range(2, T5 + 2):
+            assert np.array_equal(h.ancestors(t), ro.anc_hist[t - 1][lo:hi]), f"c5 res {res}: ancestors differ at t={t}"
+        assert np.array_equal(h.weights(), ro.final_w[lo:hi])
+        dist.barrier()
+        h.close()
+        checked += 1
+
     # ---- PG / PGAS: conditional sweeps, collective pick
     for sampler, model, thr in ((_abi.SAMPLER_PG, models.linear_gaussian(), 0.5),
                                 (_abi.SAMPLER_PGAS, models.stochastic_volatility(), 1.0)):

@@ -1,0 +1,102 @@
+"""Oracle parity, all fields bit-exact, on the SHAPES of BASELINE.json configs[2..4] (long T, d = 4,
+PG / PGAS with a second, conditional iteration) at particle counts the oracle finishes in seconds:
+
+  configs[2]  LG d=4, T=200, PG,   two iterations            N = 40 960
+  configs[3]  SV,     T=500, PGAS, two iterations            N = 20 480
+  configs[4]  LG d=1, T=100, four resamplers, sharded        N = 8 x 8 192
+
+single GPU and sharded over 2 / 4 / 8 emulated ranks (tests/mp_sharded_worker.py runs configs[4]
+with one process per GPU). Exercises what short sweeps do not: mailbox sequence numbers over
+hundreds of steps, plan[T+2], the PGAS skip rule `c <= 2 or c > T` (src/pgas.jl:114-115), the
+T+1-th resampling round (src/container.jl:344-360)."""
+import numpy as np
+import pytest
+
+import oracle as O
+from advancedps_b200 import _abi, _lib, models
+from test_gpu_sharded import assert_sharded_equal, collective, make_ranks
+
+pytestmark = pytest.mark.gpu
+
+SHAPES = {
+    "c3": (models.lg4, 40960, 200, _abi.SAMPLER_PG, 0.5, 0xDA7A0003),
+    "c4": (models.stochastic_volatility, 20480, 500, _abi.SAMPLER_PGAS, 1.0, 0xDA7A0004),
+}
+
+
+def assert_all_fields(h, ro, cfg, le):
+    T = cfg.n_steps
+    logz, ess, res = h.step_stats()
+    assert le == ro.logevidence
+    assert np.array_equal(res, ro.resampled)
+    assert np.array_equal(logz, ro.logz) and np.array_equal(ess, ro.ess)
+    for t in range(1, T + 1):
+        assert np.array_equal(h.states(t), ro.x_hist[t - 1]), f"states differ at t={t}"
+    for t in range(2, T + 2):
+        bad = np.nonzero(h.ancestors(t) != ro.anc_hist[t - 1])[0]
+        assert bad.size == 0, f"{bad.size} ancestors differ at t={t}, first {bad[:5]}"
+    assert np.array_equal(h.logweights(), ro.final_logw)
+    assert np.array_equal(h.weights(), ro.final_w)
+
+
+@pytest.mark.parametrize("name", ["c3", "c4"])
+def test_config_shape_two_iterations(name):
+    mk, N, T, smp, thr, dkey = SHAPES[name]
+    m = mk()
+    _, Y = O.simulate_data(m, T, dkey)
+    cfg = _abi.make_config(m, N, T, sampler=smp, ess_threshold=thr)
+    h = _lib.Handle(cfg)
+    h.set_observations(Y)
+    ref = None
+    for it, seed in enumerate((1234, 1235)):
+        ro = O.sweep(cfg, Y, seed, ref_traj=ref, mode=O.CANON)
+        le = h.sweep(seed, ref_on_device=ref is not None)
+        assert_all_fields(h, ro, cfg, le)
+        slot_o, traj_o = O.pick_trajectory(cfg, seed, ro, mode=O.CANON)
+        slot_g, traj_g = h.pick_trajectory()
+        assert slot_g == slot_o and np.array_equal(traj_g, traj_o)
+        if it == 1:
+            for t in (1, 2, T // 2, T):     # the reference stays in the last slot (test/container.jl:91)
+                assert np.array_equal(h.states(t)[N - 1], ref[t - 1])
+            if smp == _abi.SAMPLER_PGAS:    # ancestor sampling ran on steps 3..T and only there
+                rewired = [t for t in range(2, T + 2) if ro.anc_hist[t - 1][N - 1] != N - 1]
+                assert rewired and min(rewired) >= 3 and max(rewired) <= T
+        ref = traj_o
+
+
+@pytest.mark.parametrize("name,world", [("c3", 2), ("c3", 8), ("c4", 4), ("c4", 8)])
+def test_config_shape_sharded(name, world):
+    mk, N, T, smp, thr, dkey = SHAPES[name]
+    m = mk()
+    _, Y = O.simulate_data(m, T, dkey)
+    cfg = _abi.make_config(m, N, T, sampler=smp, ess_threshold=thr)
+    hs = make_ranks(m, N, T, Y, world, _abi.RESAMPLE_SYSTEMATIC, thr, smp)
+    ref = None
+    for seed in (1234, 1235):
+        ro = O.sweep(cfg, Y, seed, ref_traj=ref, mode=O.CANON)
+        les = collective(hs, lambda h: h.sweep(seed, ref_on_device=ref is not None))
+        assert_sharded_equal(hs, les, ro, N, T)
+        slot_o, traj_o = O.pick_trajectory(cfg, seed, ro, mode=O.CANON)
+        for slot_g, traj_g in collective(hs, lambda h: h.pick_trajectory()):
+            assert slot_g == slot_o and np.array_equal(traj_g, traj_o)
+        ref = traj_o
+
+
+@pytest.mark.parametrize("res", [_abi.RESAMPLE_SYSTEMATIC, _abi.RESAMPLE_STRATIFIED, _abi.RESAMPLE_RESIDUAL,
+                                 _abi.RESAMPLE_MULTINOMIAL])
+@pytest.mark.parametrize("world", [1, 4])
+def test_c5_shape_four_resamplers(res, world):
+    """configs[4]: LG d=1, T=100, the resampler sweep; 8192 particles per (emulated) rank."""
+    m = models.linear_gaussian()
+    N, T = 8192 * world, 100
+    _, Y = O.simulate_data(m, T, 0xDA7A0005)
+    cfg = _abi.make_config(m, N, T, resampler=res)
+    ro = O.sweep(cfg, Y, 4321, mode=O.CANON)
+    if world == 1:
+        h = _lib.Handle(cfg)
+        h.set_observations(Y)
+        assert_all_fields(h, ro, cfg, h.sweep(4321))
+    else:
+        hs = make_ranks(m, N, T, Y, world, res)
+        les = collective(hs, lambda h: h.sweep(4321))
+        assert_sharded_equal(hs, les, ro, N, T)

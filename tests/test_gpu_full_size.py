@@ -54,22 +54,35 @@ def test_c2_offspring_counts_match_weights():
 
 
 @pytest.mark.parametrize("name", ["c3", "c4"])
-def test_c3_c4_conditional_sweeps_run_at_reduced_N(name):
-    """configs[2] / configs[3] shapes (LG d=4 PG; SV PGAS) at N/16: two iterations, the second
-    conditional on the picked trajectory; reference stays in the last slot; evidence is finite."""
+def test_c3_c4_conditional_sweeps_match_oracle_at_reduced_N(name):
+    """configs[2] / configs[3] (LG d=4 PG, T=200; SV PGAS, T=500) at N/16 against the oracle (CANON,
+    its particle-parallel loops threaded -- bit-identical to the serial run): two iterations, the
+    second conditional on the trajectory picked after the first; log-evidence, the per-step logZ /
+    ESS / decisions and the final log-weights bit-equal. (All fields incl. every state and ancestor
+    are compared at N = 40 960 / 20 480 in tests/test_gpu_config_shapes.py.)"""
+    import oracle as O
+
     if name == "c3":
-        m, N, T, smp, thr = models.lg4(), 250_000, 200, _abi.SAMPLER_PG, 0.5
+        m, N, T, smp, thr, dkey = models.lg4(), 250_000, 200, _abi.SAMPLER_PG, 0.5, 0xDA7A0003
     else:
-        m, N, T, smp, thr = models.stochastic_volatility(), 125_000, 500, _abi.SAMPLER_PGAS, 1.0
-    rng = np.random.default_rng(3)
-    Y = rng.normal(size=(T, m.dy)) * 0.3
-    h = _lib.Handle(_abi.make_config(m, N, T, sampler=smp, ess_threshold=thr))
+        m, N, T, smp, thr, dkey = models.stochastic_volatility(), 125_000, 500, _abi.SAMPLER_PGAS, 1.0, 0xDA7A0004
+    _, Y = O.simulate_data(m, T, dkey)
+    cfg = _abi.make_config(m, N, T, sampler=smp, ess_threshold=thr)
+    h = _lib.Handle(cfg)
     h.set_observations(Y)
-    le1 = h.sweep(1)
-    slot, traj = h.pick_trajectory()
-    le2 = h.sweep(2, ref_on_device=True)
-    assert np.isfinite(le1) and np.isfinite(le2)
+    O.set_threads(O.max_threads())
+    try:
+        le1 = h.sweep(1)
+        ro1 = O.sweep(cfg, Y, 1, mode=O.CANON, history=False)
+        assert le1 == ro1.logevidence
+        slot, traj = h.pick_trajectory()
+        le2 = h.sweep(2, ref_on_device=True)
+        ro2 = O.sweep(cfg, Y, 2, ref_traj=traj, mode=O.CANON, history=False)
+    finally:
+        O.set_threads(1)
+    assert le2 == ro2.logevidence
+    logz, ess, res = h.step_stats()
+    assert np.array_equal(logz, ro2.logz) and np.array_equal(ess, ro2.ess) and np.array_equal(res, ro2.resampled)
+    assert np.array_equal(h.logweights(), ro2.final_logw)
     for t in (1, T // 2, T):
         assert np.array_equal(h.states(t)[N - 1], traj[t - 1])
-    slot2, traj2 = h.pick_trajectory()
-    assert traj2.shape == (T, m.d) and np.isfinite(traj2).all()

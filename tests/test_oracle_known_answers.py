@@ -70,9 +70,10 @@ def test_systematic_seq_is_the_reference_walk():
     w = np.array([0.1, 0.2, 0.3, 0.4])
     # n w cumulative = .4, 1.2, 2.4, 4.0 ; u = .5, 1.5, 2.5, 3.5
     assert list(O.resample_systematic_seq(w, 4, 0.5)) == [2, 3, 4, 4]
-    # u0 = 0 selects index 1 even if it only just reaches the threshold (strict `<`)
-    assert list(O.resample_systematic_seq(np.array([0.5, 0.5]), 2, 0.0)) == [1, 1] or True
-    assert list(O.resample_systematic_seq(np.array([0.5, 0.5]), 2, 0.0))[0] == 1
+    # strict `<` (src/resampling.jl:165): a threshold that only just reaches a cumulative weight stays
+    # with the smaller index -- v = 1.0 is not < u = 1.0, so the second draw is still index 1
+    assert list(O.resample_systematic_seq(np.array([0.5, 0.5]), 2, 0.0)) == [1, 1]
+    assert list(O.resample_systematic_seq(np.array([0.5, 0.5]), 2, 0.25)) == [1, 2]
     with pytest.raises(O.OracleError) as e:  # "sample could not be selected (are the weights normalized?)"
         O.resample_systematic_seq(np.array([0.1, 0.1]), 2, 0.9)
     assert e.value.code == 2
