@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "aps_kernels.cuh"
+#include "aps_fused.cuh"
 
 // ------------------------------------------------------------------ errors
 static thread_local std::string g_err;
@@ -93,6 +94,23 @@ static res_fn pick_resample(int kind, bool multi = false, bool defer = false) {
     if (multi) return strat ? k_resample<APS_RESAMPLE_STRATIFIED, true, false> : k_resample<APS_RESAMPLE_SYSTEMATIC, true, false>;
     if (defer) return strat ? k_resample<APS_RESAMPLE_STRATIFIED, false, true> : k_resample<APS_RESAMPLE_SYSTEMATIC, false, true>;
     return strat ? k_resample<APS_RESAMPLE_STRATIFIED, false, false> : k_resample<APS_RESAMPLE_SYSTEMATIC, false, false>;
+}
+
+// the fused persistent sweep (aps_fused.cuh): one instantiation per (model family, resampler)
+typedef void (*fused_fn)(const DevCtx, const FusedArgs);
+template <int KIND>
+static fused_fn pick_fused_kind(int obs, int d, int dy) {
+    if (d != 1) return nullptr;   // state dimension 1 (LG1 / SV / constant likelihood); d > 1 runs the three-kernel path
+    switch (obs) {
+        case APS_OBS_LINEAR_GAUSS: return dy == 1 ? k_sweep_fused<1, 1, APS_OBS_LINEAR_GAUSS, KIND> : nullptr;
+        case APS_OBS_STOCH_VOL: return k_sweep_fused<1, 1, APS_OBS_STOCH_VOL, KIND>;
+        default: return k_sweep_fused<1, 1, APS_OBS_CONST, KIND>;
+    }
+}
+static fused_fn pick_fused(int kind, int obs, int d, int dy) {
+    if (kind == APS_RESAMPLE_SYSTEMATIC) return pick_fused_kind<APS_RESAMPLE_SYSTEMATIC>(obs, d, dy);
+    if (kind == APS_RESAMPLE_STRATIFIED) return pick_fused_kind<APS_RESAMPLE_STRATIFIED>(obs, d, dy);
+    return nullptr;
 }
 
 // ------------------------------------------------------------------ TMA descriptor of the integer-weight array
@@ -226,6 +244,11 @@ struct aps_handle {
     unsigned long long epoch, pick_seq;
     float last_ms;
     long long last_launches, graph_nodes;
+    // fused persistent sweep (single GPU, systematic / stratified): kernel, geometry, exchange arrays
+    fused_fn f_fused;
+    FusedArgs fa;
+    int fused_grid, fused_threads, fused_smem;
+    bool last_fused;
     // stepwise container (aps_pc_*): reweights done so far, decision points settled so far
     bool pc_active;
     long long pc_t, pc_decided;
@@ -267,6 +290,11 @@ static void free_handle(aps_handle *h) {
     for (int i = 0; i < h->n_ipc_opened; ++i) cudaIpcCloseMemHandle(h->ipc_opened[i]);
     cudaFree(h->d_mail);
     cudaFree(h->d_peers);
+    cudaFree(h->fa.ex_max);
+    cudaFree(h->fa.ex_pmax);
+    cudaFree(h->fa.ex_tot);
+    cudaFree(h->fa.tile_tot);
+    cudaFree(h->fa.qp);
     if (h->h_weights) cudaFreeHost(h->h_weights);
     if (h->h_sp) cudaFreeHost(h->h_sp);
     if (h->h_st) cudaFreeHost(h->h_st);
@@ -404,6 +432,53 @@ extern "C" int aps_create(const aps_config *cfg, aps_handle **out) {
     h->f_psel = pick_pgas_select(d);
     prefer_max_smem(h->f_pmax);
     prefer_max_smem(h->f_psel);
+    // ---- fused persistent sweep: one CTA per SM, every CTA owns a contiguous chunk of slots
+    h->f_fused = nullptr;
+    if (world == 1 && getenv("APS_NO_FUSED") == nullptr) {
+        int coop = 0;
+        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, cfg->device);
+        fused_fn fn = coop ? pick_fused(cfg->resampler, cfg->model.obs_kind, d, cfg->model.dy) : nullptr;
+        if (fn) {
+            long long G = (Nl + 63) / 64;
+            if (G > sm_count()) G = sm_count();
+            long long Nc = ((Nl + G - 1) / G + 63) & ~63LL;
+            G = (Nl + Nc - 1) / Nc;
+            const long long P = Nc / 2;                          // slot pairs per chunk
+            const long long rounds = (P + APS_FUSED_MAX_THREADS - 1) / APS_FUSED_MAX_THREADS;
+            long long NT = (((P + rounds - 1) / rounds) + 31) & ~31LL;   // fewest idle lanes in the last round
+            if (NT < ((G + 31) & ~31LL)) NT = (G + 31) & ~31LL;
+            if (NT < 64) NT = 64;
+            if (NT > APS_FUSED_MAX_THREADS) NT = APS_FUSED_MAX_THREADS;
+            if (const char *e = getenv("APS_FUSED_THREADS")) NT = atoll(e);   // tuning experiments
+            const long long TP = NT * APS_FUSED_IPT;
+            const long long tpc = (Nc + TP - 1) / TP;
+            const int smem = (int)(NT * APS_FUSED_CPT * sizeof(int));
+            int occ = 0;
+            if (Nc <= 2147483647LL / 2 && G <= APS_FUSED_MAX_CTAS && NT >= G &&
+                cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) == cudaSuccess &&
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, (int)NT, smem) == cudaSuccess &&
+                (long long)occ * sm_count() >= G) {
+                h->f_fused = fn;
+                h->fused_grid = (int)G;
+                h->fused_threads = (int)NT;
+                h->fused_smem = smem;
+                h->fa.chunk = (int)Nc;
+                h->fa.tpc = (int)tpc;
+                CUH(cudaMalloc(&h->fa.ex_max, sizeof(ulonglong2) * (size_t)G));
+                CUH(cudaMalloc(&h->fa.ex_pmax, sizeof(ulonglong2) * (size_t)G));
+                CUH(cudaMalloc(&h->fa.ex_tot, sizeof(ulonglong2) * 3 * (size_t)G));
+                CUH(cudaMalloc(&h->fa.tile_tot, sizeof(u64) * (size_t)(G * tpc)));
+                CUH(cudaMemset(h->fa.ex_max, 0, sizeof(ulonglong2) * (size_t)G));
+                CUH(cudaMemset(h->fa.ex_pmax, 0, sizeof(ulonglong2) * (size_t)G));
+                CUH(cudaMemset(h->fa.ex_tot, 0, sizeof(ulonglong2) * 3 * (size_t)G));
+                if (cfg->sampler == APS_PGAS) {
+                    CUH(cudaMalloc(&h->fa.qp, sizeof(u64) * (size_t)c.NS));
+                    CUH(cudaMemset(h->fa.qp, 0, sizeof(u64) * (size_t)c.NS));
+                }
+            }
+            cudaGetLastError();
+        }
+    }
 #undef CUH
     *out = h;
     return APS_OK;
@@ -601,6 +676,17 @@ static int sweep_impl(aps_handle *h, uint64_t master_seed, const double *ref_tra
     LaunchProf prof;
     prof.st = h->stream;
     const bool profiled = class_ms != nullptr;
+    const bool fused = !profiled && h->f_fused != nullptr;
+    h->last_fused = fused;
+    if (fused) {
+        CU(cudaMemsetAsync(c.fat_cnt, 0, sizeof(int) * (size_t)c.fat_steps, h->stream));   // (no fat lists on this path)
+        CU(cudaEventRecord(h->ev0, h->stream));
+        void *args[2] = {(void *)&h->ctx, (void *)&h->fa};
+        CU(cudaLaunchCooperativeKernel((const void *)h->f_fused, dim3(h->fused_grid), dim3(h->fused_threads), args,
+                                       (size_t)h->fused_smem, h->stream));
+        h->last_launches = 1;
+        CU(cudaEventRecord(h->ev1, h->stream));
+    } else {
     if (!profiled && !h->graph_ready) {
         cudaGraph_t g;
         CU(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
@@ -617,6 +703,7 @@ static int sweep_impl(aps_handle *h, uint64_t master_seed, const double *ref_tra
         h->last_launches = h->graph_nodes;
     }
     CU(cudaEventRecord(h->ev1, h->stream));
+    }
     CU(cudaMemcpyAsync(h->h_st, c.st, sizeof(SweepState), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     CU(cudaGetLastError());
@@ -638,7 +725,8 @@ static int sweep_impl(aps_handle *h, uint64_t master_seed, const double *ref_tra
     h->pc_active = false;
     if (h->h_st->err)
         return fail(h->h_st->err, h->h_st->err == APS_ERR_COMM
-                                      ? "aps_sweep: a peer rank did not answer within the exchange timeout"
+                                      ? (fused ? "aps_sweep: a CTA of the persistent sweep kernel never arrived at an exchange (launch not co-resident?)"
+                                               : "aps_sweep: a peer rank did not answer within the exchange timeout")
                                       : "aps_sweep: particle weights could not be normalised (all -Inf or NaN log-weights)");
     *logevidence = h->h_st->logev;
     if (c.dbg & 16) {
@@ -848,6 +936,17 @@ extern "C" int aps_pick_trajectory(aps_handle *h, double *traj_out, int64_t *ind
     const DevCtx &c = h->ctx;
     // sharded: a collective call -- every rank picks (the ranks exchange their candidates) and
     // walks the genealogy through the peer-mapped stores, so each ends up with the trajectory
+    if (h->last_fused && !h->pc_active) {
+        // the fused sweep keeps per-chunk totals only; the pick over non-uniform final weights walks the
+        // 2048-particle tile totals / prefixes: rebuild them from the integer weights (scratch plan / acc slot)
+        DevCtx cc = c;
+        cc.st = nullptr;
+        cc.defer_plan = 0;
+        cc.acc = c.acc + (c.T + 1);
+        cc.plan = c.plan + (c.T + 1);
+        CU(cudaMemsetAsync(cc.acc, 0, sizeof(StepAcc), h->stream));
+        k_normalise<IN_Q><<<(int)c.num_tiles, APS_K2_THREADS, 0, h->stream>>>(cc, nullptr, 0);
+    }
     k_pick<<<1, APS_THREADS, 0, h->stream>>>(c, c.T, c.T + 1, APS_DOM_PICK, ++h->pick_seq);
     k_backtrace<<<1, 32, 0, h->stream>>>(c, -1, h->d_traj);
     CU(cudaMemcpyAsync(h->d_ref, h->d_traj, sizeof(double) * (size_t)c.T * c.d, cudaMemcpyDeviceToDevice, h->stream));
