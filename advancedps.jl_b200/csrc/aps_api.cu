@@ -10,6 +10,7 @@
 #include <mutex>
 #include <string>
 #include <vector>
+#include <algorithm>
 
 #include "aps_kernels.cuh"
 #include "aps_fused.cuh"
@@ -248,7 +249,7 @@ struct aps_handle {
     fused_fn f_fused;
     FusedArgs fa;
     int fused_grid, fused_threads, fused_smem;
-    bool last_fused;
+    bool last_fused, fused_forced;
     // stepwise container (aps_pc_*): reweights done so far, decision points settled so far
     bool pc_active;
     long long pc_t, pc_decided;
@@ -293,7 +294,9 @@ static void free_handle(aps_handle *h) {
     cudaFree(h->fa.ex_max);
     cudaFree(h->fa.ex_pmax);
     cudaFree(h->fa.ex_tot);
-    cudaFree(h->fa.tile_tot);
+    cudaFree(h->fa.sub_prefix);
+    cudaFree(h->fa.dbg);
+    cudaFree(h->fa.ctr);
     cudaFree(h->fa.qp);
     if (h->h_weights) cudaFreeHost(h->h_weights);
     if (h->h_sp) cudaFreeHost(h->h_sp);
@@ -434,14 +437,16 @@ extern "C" int aps_create(const aps_config *cfg, aps_handle **out) {
     prefer_max_smem(h->f_psel);
     // ---- fused persistent sweep: one CTA per SM, every CTA owns a contiguous chunk of slots
     h->f_fused = nullptr;
+    h->fused_forced = getenv("APS_FUSED") != nullptr && atoi(getenv("APS_FUSED")) != 0;
     if (world == 1 && getenv("APS_NO_FUSED") == nullptr) {
         int coop = 0;
         cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, cfg->device);
         fused_fn fn = coop ? pick_fused(cfg->resampler, cfg->model.obs_kind, d, cfg->model.dy) : nullptr;
         if (fn) {
-            long long G = (Nl + 63) / 64;
+            const long long SUB = APS_FUSED_SUB;
+            long long G = (Nl + SUB - 1) / SUB;
             if (G > sm_count()) G = sm_count();
-            long long Nc = ((Nl + G - 1) / G + 63) & ~63LL;
+            long long Nc = ((Nl + G - 1) / G + SUB - 1) / SUB * SUB;
             G = (Nl + Nc - 1) / Nc;
             const long long P = Nc / 2;                          // slot pairs per chunk
             const long long rounds = (P + APS_FUSED_MAX_THREADS - 1) / APS_FUSED_MAX_THREADS;
@@ -450,11 +455,12 @@ extern "C" int aps_create(const aps_config *cfg, aps_handle **out) {
             if (NT < 64) NT = 64;
             if (NT > APS_FUSED_MAX_THREADS) NT = APS_FUSED_MAX_THREADS;
             if (const char *e = getenv("APS_FUSED_THREADS")) NT = atoll(e);   // tuning experiments
-            const long long TP = NT * APS_FUSED_IPT;
-            const long long tpc = (Nc + TP - 1) / TP;
-            const int smem = (int)(NT * APS_FUSED_CPT * sizeof(int));
+            const long long nsub = Nc / SUB;
+            const long long smem_ll = NT * APS_FUSED_CPT * (long long)sizeof(int) + (nsub + 1) * (long long)sizeof(u64) * (1 + APS_FUSED_GRP) +
+                                      APS_FUSED_GRP * nsub * (long long)sizeof(int) + 16;
+            const int smem = (int)smem_ll;
             int occ = 0;
-            if (Nc <= 2147483647LL / 2 && G <= APS_FUSED_MAX_CTAS && NT >= G &&
+            if (Nl <= (1LL << 30) && smem_ll <= 200 * 1024 && G <= APS_FUSED_MAX_CTAS && NT >= G && NT <= APS_FUSED_MAX_THREADS &&
                 cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) == cudaSuccess &&
                 cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, (int)NT, smem) == cudaSuccess &&
                 (long long)occ * sm_count() >= G) {
@@ -463,17 +469,20 @@ extern "C" int aps_create(const aps_config *cfg, aps_handle **out) {
                 h->fused_threads = (int)NT;
                 h->fused_smem = smem;
                 h->fa.chunk = (int)Nc;
-                h->fa.tpc = (int)tpc;
+                h->fa.nsub = (int)nsub;
                 CUH(cudaMalloc(&h->fa.ex_max, sizeof(ulonglong2) * (size_t)G));
                 CUH(cudaMalloc(&h->fa.ex_pmax, sizeof(ulonglong2) * (size_t)G));
                 CUH(cudaMalloc(&h->fa.ex_tot, sizeof(ulonglong2) * 3 * (size_t)G));
-                CUH(cudaMalloc(&h->fa.tile_tot, sizeof(u64) * (size_t)(G * tpc)));
+                CUH(cudaMalloc(&h->fa.sub_prefix, sizeof(u64) * (size_t)(G * (nsub + 1))));
+                CUH(cudaMalloc(&h->fa.dbg, sizeof(u64) * 8 * (size_t)G));
+                CUH(cudaMalloc(&h->fa.ctr, sizeof(u64) * 2));
                 CUH(cudaMemset(h->fa.ex_max, 0, sizeof(ulonglong2) * (size_t)G));
                 CUH(cudaMemset(h->fa.ex_pmax, 0, sizeof(ulonglong2) * (size_t)G));
                 CUH(cudaMemset(h->fa.ex_tot, 0, sizeof(ulonglong2) * 3 * (size_t)G));
+                CUH(cudaMemset(h->fa.dbg, 0, sizeof(u64) * 8 * (size_t)G));
                 if (cfg->sampler == APS_PGAS) {
-                    CUH(cudaMalloc(&h->fa.qp, sizeof(u64) * (size_t)c.NS));
-                    CUH(cudaMemset(h->fa.qp, 0, sizeof(u64) * (size_t)c.NS));
+                    CUH(cudaMalloc(&h->fa.qp, sizeof(u64) * 2 * (size_t)c.NS));
+                    CUH(cudaMemset(h->fa.qp, 0, sizeof(u64) * 2 * (size_t)c.NS));
                 }
             }
             cudaGetLastError();
@@ -676,10 +685,18 @@ static int sweep_impl(aps_handle *h, uint64_t master_seed, const double *ref_tra
     LaunchProf prof;
     prof.st = h->stream;
     const bool profiled = class_ms != nullptr;
-    const bool fused = !profiled && h->f_fused != nullptr;
+    // Which path runs this sweep. The fused persistent kernel wins where a step is many small launches
+    // (PGAS ancestor sampling: 5 kernels per step) or the per-parent work is heavy (stratified);
+    // for the plain systematic sweep the three-kernel graph is ~20 % faster at every N measured
+    // (profiles/fused_vs_three_kernel_r02.txt), so that stays the default there.
+    // APS_FUSED=1 forces the fused kernel wherever it is eligible, APS_NO_FUSED=1 disables it.
+    bool fused = !profiled && h->f_fused != nullptr;
+    if (fused && !h->fused_forced)
+        fused = c.resampler == APS_RESAMPLE_STRATIFIED || (c.sampler == APS_PGAS && has_ref);
     h->last_fused = fused;
     if (fused) {
         CU(cudaMemsetAsync(c.fat_cnt, 0, sizeof(int) * (size_t)c.fat_steps, h->stream));   // (no fat lists on this path)
+        CU(cudaMemsetAsync(h->fa.ctr, 0, sizeof(u64) * 2, h->stream));
         CU(cudaEventRecord(h->ev0, h->stream));
         void *args[2] = {(void *)&h->ctx, (void *)&h->fa};
         CU(cudaLaunchCooperativeKernel((const void *)h->f_fused, dim3(h->fused_grid), dim3(h->fused_threads), args,
@@ -739,6 +756,19 @@ static int sweep_impl(aps_handle *h, uint64_t master_seed, const double *ref_tra
         }
         fprintf(stderr, "[aps rank %d] k_propagate first-block-start -> last-block-end: %.2f us avg; end(t-1) -> start(t): %.2f us avg\n",
                 c.rank, span / c.T * 1e-3, gap / (c.T - 1) * 1e-3);
+    }
+    if (fused && (c.dbg & 32)) {   // per-phase time of every CTA (ns, summed over the sweep): min / median / max over the CTAs
+        std::vector<u64> d((size_t)h->fused_grid * 8);
+        cudaMemcpy(d.data(), h->fa.dbg, sizeof(u64) * d.size(), cudaMemcpyDeviceToHost);
+        static const char *nm[5] = {"A propagate", "exchange 1", "B quantise", "exchange 2 + plan", "C pull-resample"};
+        fprintf(stderr, "[aps fused] %d CTAs x %d threads, chunk %d, %d sub-tiles; us per step (min / median / max over CTAs)\n",
+                h->fused_grid, h->fused_threads, h->fa.chunk, h->fa.nsub);
+        for (int k = 0; k < 5; ++k) {
+            std::vector<double> v;
+            for (int g = 0; g < h->fused_grid; ++g) v.push_back(d[(size_t)g * 8 + k] * 1e-3 / (double)c.T);
+            std::sort(v.begin(), v.end());
+            fprintf(stderr, "[aps fused]   %-18s %7.2f %7.2f %7.2f\n", nm[k], v.front(), v[v.size() / 2], v.back());
+        }
     }
     if (getenv("APS_DEBUG_SPIN") && c.world > 1)
         fprintf(stderr, "[aps rank %d] block-0 wait cycles per sweep: max-exchange %llu, totals %llu, scatter-done %llu (T=%lld)\n",

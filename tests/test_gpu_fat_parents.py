@@ -20,11 +20,10 @@ def low_fat_threshold(monkeypatch):
 
 @pytest.fixture(params=["fused", "three-kernel"])
 def sweep_path(request, monkeypatch):
-    """Single-GPU systematic / stratified sweeps run as the fused persistent kernel, which resolves
-    ancestors per child slot ("pull") and needs no fat-parent lists; APS_NO_FUSED=1 selects the
-    three-kernel path, where the lists exist. Both must equal the oracle under degenerate weights."""
-    if request.param == "three-kernel":
-        monkeypatch.setenv("APS_NO_FUSED", "1")
+    """The fused persistent kernel (forced with APS_FUSED=1) resolves ancestors per child slot ("pull")
+    and needs no fat-parent lists; APS_NO_FUSED=1 selects the three-kernel path, where the lists exist.
+    Both must equal the oracle under degenerate weights."""
+    monkeypatch.setenv("APS_NO_FUSED" if request.param == "three-kernel" else "APS_FUSED", "1")
     return request.param
 
 

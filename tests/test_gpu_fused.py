@@ -1,7 +1,9 @@
-"""The fused persistent sweep kernel (csrc/aps_fused.cuh): single-GPU systematic / stratified sweeps
-of the d = 1 families run as ONE cooperative launch -- checked here to be the path that runs, to
-equal the oracle on shapes the other parity tests do not reach (several expand passes per CTA,
-two-slab history, many sweeps on one handle), and to equal the three-kernel path bit for bit."""
+"""The fused persistent sweep kernel (csrc/aps_fused.cuh): a single-GPU systematic / stratified sweep
+of the d = 1 families as ONE cooperative launch. By default it runs where it is the faster path
+(PGAS conditional sweeps, stratified resampling); APS_FUSED=1 forces it everywhere it is eligible,
+which is how this module checks it against the oracle on shapes the other parity tests do not reach
+(several expand passes per CTA, two-slab history, many sweeps on one handle) and against the
+three-kernel path bit for bit."""
 import numpy as np
 import pytest
 
@@ -10,6 +12,11 @@ from advancedps_b200 import _abi, _lib, models
 from test_gpu_sweep_parity import assert_sweep_equal
 
 pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(autouse=True)
+def force_fused(monkeypatch):
+    monkeypatch.setenv("APS_FUSED", "1")
 
 
 def handle(m, N, T, Y, **kw):
@@ -28,6 +35,26 @@ def test_fused_is_the_path_that_runs():
     h = handle(m, 5000, 5, Y, resampler=_abi.RESAMPLE_MULTINOMIAL)
     h.sweep(1)
     assert h.last_sweep_launches() > 5      # multinomial / residual: the per-step kernels
+
+
+def test_default_dispatch(monkeypatch):
+    """Without APS_FUSED: fused for stratified resampling and for PGAS sweeps that condition on a
+    reference (5 launches per step otherwise), the three-kernel graph for the rest."""
+    monkeypatch.delenv("APS_FUSED")
+    lg, sv = models.linear_gaussian(), models.stochastic_volatility()
+    _, Y = O.simulate_data(lg, 6, 1)
+    h = handle(lg, 5000, 6, Y)
+    h.sweep(1)
+    assert h.last_sweep_launches() == 3 * 6 + 2
+    h = handle(lg, 5000, 6, Y, resampler=_abi.RESAMPLE_STRATIFIED)
+    h.sweep(1)
+    assert h.last_sweep_launches() == 1
+    h = handle(sv, 5000, 6, Y, sampler=_abi.SAMPLER_PGAS, ess_threshold=1.0)
+    h.sweep(1)
+    assert h.last_sweep_launches() > 1      # unconditional first sweep: nothing for ancestor sampling to do
+    h.pick_trajectory()
+    h.sweep(2, ref_on_device=True)
+    assert h.last_sweep_launches() == 1
 
 
 @pytest.mark.parametrize("N,T,res,thr", [
@@ -98,6 +125,7 @@ def test_fused_equals_three_kernel_path(case, monkeypatch):
     hf = handle(m, N, T, Y, resampler=res, ess_threshold=thr, sampler=smp)
     lef = hf.sweep(5, ref_traj=ref)
     assert hf.last_sweep_launches() == 1
+    monkeypatch.delenv("APS_FUSED")
     monkeypatch.setenv("APS_NO_FUSED", "1")
     hk = handle(m, N, T, Y, resampler=res, ess_threshold=thr, sampler=smp)
     lek = hk.sweep(5, ref_traj=ref)
