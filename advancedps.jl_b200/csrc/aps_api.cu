@@ -704,7 +704,12 @@ static int sweep_impl(aps_handle *h, uint64_t master_seed, const double *ref_tra
         h->last_launches = 1;
         CU(cudaEventRecord(h->ev1, h->stream));
     } else {
-    if (!profiled && !h->graph_ready) {
+    // APS_NO_GRAPH=1: launch the per-step kernels directly instead of replaying a CUDA graph. Needed
+    // only where several ranks are EMULATED on one GPU with long sweeps (tests): graphs of > ~1000
+    // nodes from different streams were observed not to run concurrently, and ranks that spin on
+    // each other then never meet. One process per GPU -- the product path -- replays the graph.
+    const bool no_graph = getenv("APS_NO_GRAPH") != nullptr;
+    if (!profiled && !no_graph && !h->graph_ready) {
         cudaGraph_t g;
         CU(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
         h->graph_nodes = enqueue_sweep(h);
@@ -715,6 +720,7 @@ static int sweep_impl(aps_handle *h, uint64_t master_seed, const double *ref_tra
     }
     CU(cudaEventRecord(h->ev0, h->stream));
     if (profiled) h->last_launches = enqueue_sweep(h, &prof);
+    else if (no_graph) h->last_launches = enqueue_sweep(h);
     else {
         CU(cudaGraphLaunch(h->graph, h->stream));
         h->last_launches = h->graph_nodes;

@@ -119,30 +119,54 @@ __device__ __forceinline__ void st_sys_u64(u64 *p, u64 v) {
 // their LOCAL mailbox until every rank's values for the expected sequence number are there.
 //
 // Memory model. A value travels with its sequence number in ONE 128-bit access (st / ld .b128:
-// single-copy atomic), the post is a RELEASE at system scope (everything the posting thread
-// observed before it -- its block's and, across the kernel boundary, the previous kernel's peer
-// stores -- is visible to whoever acquires the pair) and the successful poll is an ACQUIRE; the
-// __syncthreads() that follows every wait extends the edge to the rest of the consumer block. The
-// data path itself (ancestor scatter, state gathers, fat-list entries) stays plain / relaxed.
+// single-copy atomic), so an exchange of VALUES (maxima, integer totals, candidates: every kind
+// but 2) needs no ordering against other memory at all: the consumer validates each pair by its
+// sequence number and uses nothing else the producer wrote. Those posts and polls are relaxed.
+//
+// Kind 2 is different: it is a barrier that publishes DATA written with plain peer stores -- the
+// ancestor scatter and the fat-list pushes of the previous resample kernel. It is posted by block
+// 0 of the NEXT kernel of the stream (the previous kernel, including its peer stores, is complete
+// by then) with a RELEASE store at system scope, which is cheap there: a block that has just
+// started has nothing outstanding to drain. On the consumer side the poll is relaxed and the
+// peer-written data (ancestor slab, fat entries and counts) is read with L1-bypassing loads
+// (ld.global.cg): L2 is the point of coherence for peer writes, and the writes were performed
+// there before the flag was even sent.
+//
+// The textbook alternative -- an acquire per poll, or one fence.acq_rel.sys after the wait in every
+// block -- was built and measured (round 2, 2 x B200, bench workload): acquire loads 4.70 ms per
+// sweep, relaxed poll + one fence per block 7.55 ms, this scheme 3.6 ms (profiles/README.md). A
+// system-scope fence in each of the ~1200 blocks of a step drains the whole SM every time.
+// -DAPS_STRICT_FENCES=1 builds the fenced variant; tests/test_gpu_stress.py passes under both.
+#ifndef APS_STRICT_FENCES
+#define APS_STRICT_FENCES 0
+#endif
 __device__ __forceinline__ void st_pair_sys(ulonglong2 *p, u64 v, u64 seq) {
+    asm volatile("{ .reg .b128 t; mov.b128 t, {%1, %2}; st.relaxed.sys.global.b128 [%0], t; }" ::"l"(p), "l"(v), "l"(seq)
+                 : "memory");
+}
+__device__ __forceinline__ void st_pair_sys_release(ulonglong2 *p, u64 v, u64 seq) {
     asm volatile("{ .reg .b128 t; mov.b128 t, {%1, %2}; st.release.sys.global.b128 [%0], t; }" ::"l"(p), "l"(v), "l"(seq)
                  : "memory");
 }
 __device__ __forceinline__ ulonglong2 ld_pair_sys(const ulonglong2 *p) {
     ulonglong2 r;
-    asm volatile("{ .reg .b128 t; ld.acquire.sys.global.b128 t, [%2]; mov.b128 {%0, %1}, t; }"
+    asm volatile("{ .reg .b128 t; ld.relaxed.sys.global.b128 t, [%2]; mov.b128 {%0, %1}, t; }"
                  : "=l"(r.x), "=l"(r.y)
                  : "l"(p)
                  : "memory");
     return r;
 }
+__device__ __forceinline__ void fence_acq_rel_sys() { asm volatile("fence.acq_rel.sys;" ::: "memory"); }
 // publish nv values of this rank (threads 0..world-1 of ONE block; thread r writes to rank r)
 __device__ __forceinline__ void mail_post(const PeerTable *pt, int rank, int world, int kind, u64 seq, const u64 *v,
                                           int nv) {
     const int r = threadIdx.x;
     if (r < world) {
         MailSlot *dst = pt->mail[r] + kind * APS_MAX_RANKS + rank;
-        for (int k = 0; k < nv; ++k) st_pair_sys(&dst->pair[k], v[k], seq);
+        if (kind == 2 || APS_STRICT_FENCES)
+            for (int k = 0; k < nv; ++k) st_pair_sys_release(&dst->pair[k], v[k], seq);
+        else
+            for (int k = 0; k < nv; ++k) st_pair_sys(&dst->pair[k], v[k], seq);
     }
 }
 // Spin budget of one wait, in SM cycles (~2 GHz): APS_COMM_TIMEOUT_MS, default 3000 ms. A dead peer
@@ -175,6 +199,9 @@ __device__ __forceinline__ bool mail_wait(const PeerTable *pt, int rank, int wor
             }
             out[r][k] = pr.x;
         }
+#if APS_STRICT_FENCES
+        fence_acq_rel_sys();   // acquire: orders everything after the wait behind the producers' release stores
+#endif
         if (spin && kind < 4 && blockIdx.x == 0 && r == (rank + 1) % world)
             atomicAdd(&spin[kind], (unsigned long long)(clock64() - t0));
     }

@@ -119,7 +119,7 @@ __global__ void APS_K1_BOUNDS k_propagate(const __grid_constant__ DevCtx c, cons
     // (a separate pre-pass keeps the lookup out of the main loop's register budget).
     auto resolve_fat = [&]() {
         if (t <= 1) return;
-        int nfat = c.fat_cnt[t - 1];
+        int nfat = MULTI ? __ldcg(&c.fat_cnt[t - 1]) : c.fat_cnt[t - 1];   // (sharded: pushed by the peers, read at L2)
         if (!nfat) return;
         if (nfat > APS_FAT_MAX) nfat = APS_FAT_MAX;
         const FatEntry *fatl = c.fat + (t - 1) * APS_FAT_MAX;
@@ -163,7 +163,8 @@ __global__ void APS_K1_BOUNDS k_propagate(const __grid_constant__ DevCtx c, cons
         if (!first) aps_pair_normals<D>(key, (u64)(pair0 + p), (u64)t, z);
         const long long i0 = 2 * p;
         int2 a2 = make_int2(0, 0);
-        if (t > 1) a2 = *reinterpret_cast<const int2 *>(anc + i0);
+        if (t > 1) a2 = MULTI ? __ldcg(reinterpret_cast<const int2 *>(anc + i0))   // scattered by the peers: read at L2
+                              : *reinterpret_cast<const int2 *>(anc + i0);
         double2 lw2 = make_double2(0.0, 0.0);
         if (!reset) lw2 = *reinterpret_cast<const double2 *>(c.logw + i0);
         double xo[2][D];
@@ -1873,12 +1874,16 @@ __global__ void __launch_bounds__(APS_K1_THREADS) k_fill_fat(const __grid_consta
         if (!(c.dbg & 1) && !mail_wait(c.peers, c.rank, c.world, 2, seq, s_w, 1, nullptr, &c.st->err)) c.st->err = APS_ERR_COMM;
         __syncthreads();
     }
-    int nfat = c.fat_cnt[s];
+    int nfat = __ldcg(&c.fat_cnt[s]);
     if (nfat > APS_FAT_MAX) nfat = APS_FAT_MAX;
     // this rank's child slots (operator level: n_override children drawn from N weights)
     const long long lo_r = c.slot0, hi_r = c.slot0 + (c.n_override > 0 ? c.n_override : c.N);
     for (int e = 0; e < nfat; ++e) {
-        const FatEntry f = c.fat[s * APS_FAT_MAX + e];
+        const int4 fv = __ldcg(reinterpret_cast<const int4 *>(c.fat + s * APS_FAT_MAX + e));
+        FatEntry f;
+        f.lo = fv.x;
+        f.hi = fv.y;
+        f.parent = fv.z;
         const long long lo = f.lo > lo_r ? f.lo : lo_r, hi = f.hi < hi_r ? f.hi : hi_r;
         for (long long g = lo + (long long)blockIdx.x * APS_K1_THREADS + threadIdx.x; g < hi;
              g += (long long)gridDim.x * APS_K1_THREADS)
