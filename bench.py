@@ -120,11 +120,15 @@ def run_reference(args, rank, emit=print):
     import oracle as O
     from advancedps_b200 import _abi, models
 
-    n_sample = env_int("APS_BENCH_REF_N", 200_000)
+    # the full workload (N = 1e6: ~6.5 s per sweep on one core) whenever steps + warm-up fit in ~2.5 minutes,
+    # else the largest N (a multiple of 1000) that does; one warm-up sweep is enough on a CPU
+    warm = min(args.warmup, 1)
+    budget_n = int(150.0 / (6.5 * (args.steps + warm)) * N_PARTICLES) // 1000 * 1000
+    n_sample = env_int("APS_BENCH_REF_N", max(1000, min(N_PARTICLES, budget_n)))
     m = models.linear_gaussian()
     Y = make_data()
     cfg = _abi.make_config(m, n_sample, T_STEPS)
-    for _ in range(args.warmup):
+    for _ in range(warm):
         O.sweep(cfg, Y, MASTER_SEED, mode=O.SEQ, history=True)
     t0 = time.perf_counter()
     for k in range(args.steps):
@@ -132,7 +136,7 @@ def run_reference(args, rank, emit=print):
     dt = time.perf_counter() - t0
     value = n_sample * T_STEPS * args.steps / dt
     sample = (f"N={n_sample} of 1e6 particles, full T={T_STEPS}, oracle port in SEQ (reference fp64 order) mode, "
-              f"1 thread of {os.cpu_count()} host cores")
+              f"1 thread of {os.cpu_count()} host cores ({warm} warm-up sweep)")
     out = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
@@ -145,28 +149,117 @@ def run_reference(args, rank, emit=print):
     emit(json.dumps(out))
 
 
-def oracle_check(seed, logev_gpu):
-    """The first half of the parity claim at the FULL bench size: the oracle (CANON mode, the
-    arithmetic the GPU reproduces) run once with the seed of the last timed sweep. The run uses all
-    host threads for the oracle's particle-parallel loops (bit-identical to the serial run), which
-    also gives an all-cores CPU figure next to the single-thread cpu_baseline."""
+def oracle_check(seed, logev_gpu, world=1, handle=None):
+    """The parity claim at the FULL bench size, inside the driver-run line. The oracle (CANON mode,
+    the arithmetic the GPU reproduces) runs once with the seed of the last timed sweep, at
+    world x 1e6 particles, its particle-parallel loops on all host threads (bit-identical to the
+    serial run; also an all-cores CPU figure for context). With `handle` (1 GPU: the handle still
+    holds that sweep's genealogy) every ancestor index of all T+1 resampling rounds is compared:
+    `ancestor_diff_vs_canon` must be 0; `ancestor_diff_vs_seq` counts the differences against the
+    oracle's SEQ mode -- the reference's sequential fp64 order (src/resampling.jl:157-179) -- and
+    is reported, not asserted."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import numpy as np
+
     import oracle as O
     from advancedps_b200 import _abi, models
 
-    cfg = _abi.make_config(models.linear_gaussian(), N_PARTICLES, T_STEPS)
+    n = N_PARTICLES * world
+    cfg = _abi.make_config(models.linear_gaussian(), n, T_STEPS)
     nthr = O.max_threads()
     O.set_threads(nthr)
+    want_anc = handle is not None
     t0 = time.perf_counter()
-    ro = O.sweep(cfg, make_data(), seed, mode=O.CANON, history=False)
+    ro = O.sweep(cfg, make_data(), seed, mode=O.CANON, history=want_anc)
     dt = time.perf_counter() - t0
     O.set_threads(1)
-    return {"oracle_canon": ro.logevidence, "abs_err": abs(logev_gpu - ro.logevidence),
-            "rel_err": abs(logev_gpu - ro.logevidence) / abs(ro.logevidence), "tolerance": 1e-6,
-            "cpu_all_cores": {"value": N_PARTICLES * T_STEPS / dt, "unit": UNIT, "cores": nthr, "kind": "port",
-                              "sample": f"one full sweep in {dt:.1f} s; oracle CANON mode with its particle-parallel "
-                                        "loops threaded (the resampling walk stays serial) -- NOT the reference's "
-                                        "structure, which is single-threaded; an upper bound for context"}}
+    out = {"oracle_canon": ro.logevidence, "abs_err": abs(logev_gpu - ro.logevidence),
+           "rel_err": abs(logev_gpu - ro.logevidence) / abs(ro.logevidence), "tolerance": 1e-6,
+           "n_particles": n,
+           "cpu_all_cores": {"value": n * T_STEPS / dt, "unit": UNIT, "cores": nthr, "kind": "port",
+                             "sample": f"one full sweep in {dt:.1f} s; oracle CANON mode with its particle-parallel "
+                                       "loops threaded (the resampling walk stays serial) -- NOT the reference's "
+                                       "structure, which is single-threaded; an upper bound for context"}}
+    if want_anc:
+        anc = [handle.ancestors(t) for t in range(2, T_STEPS + 2)]
+        diff_canon = int(sum(int((a != ro.anc_hist[t + 1]).sum()) for t, a in enumerate(anc)))
+        states_equal = bool(all(np.array_equal(handle.states(t), ro.x_hist[t - 1]) for t in (1, T_STEPS // 2, T_STEPS)))
+        del ro
+        rs = O.sweep(cfg, make_data(), seed, mode=O.SEQ, history=True)
+        per_step = [int((a != rs.anc_hist[t + 1]).sum()) for t, a in enumerate(anc)]
+        first = next((t + 1 for t, d in enumerate(per_step) if d), None)
+        out.update({
+            "ancestor_diff_vs_canon": diff_canon, "ancestor_indices_compared": n * T_STEPS,
+            "states_equal_vs_canon": states_equal,
+            "ancestor_diff_vs_seq": int(sum(per_step)), "first_step_differing_vs_seq": first,
+            "steps_differing_vs_seq": int(sum(1 for d in per_step if d)),
+            "logevidence_seq": rs.logevidence, "abs_err_vs_seq": abs(logev_gpu - rs.logevidence),
+            "note": "CANON = exact-integer weights (what the CUDA path computes): target 0 differences. SEQ = the "
+                    "reference's sequential fp64 order with the same Philox draws: a threshold within rounding distance "
+                    "of a cumulative weight can fall on the other side; once one ancestor differs the two particle "
+                    "systems are different samples of the same law, so later steps differ wholesale -- the count is "
+                    "reported, `first_step_differing_vs_seq` says where the first flip happened."})
+    return out
+
+
+def config_block(world, rank, local_rank, barrier):
+    """Device time of one sweep of the other BASELINE.json configs at their full sizes, so that they are
+    driver-witnessed: configs[2] (LG d=4, T=200, N=4e6, PG: second, conditional iteration), configs[3] (SV,
+    T=500, N=2e6, PGAS: second iteration with ancestor sampling), configs[4] resampler sweep at this
+    run's GPU count (N = n_gpus x 1e6, T=100; stratified / residual / multinomial -- systematic is the headline)."""
+    import numpy as np
+
+    from advancedps_b200 import _abi, _lib, models
+
+    out = {}
+    rng = np.random.default_rng(0)
+
+    def timed(h, cond, iters=2):
+        h.sweep(1)
+        if cond:
+            h.pick_trajectory()
+        ms = []
+        for k in range(iters):
+            h.sweep(2 + k, ref_on_device=cond)
+            ms.append(h.last_sweep_ms())
+            if cond:
+                h.pick_trajectory()
+        return min(ms), h.last_sweep_launches()
+
+    if world == 1:
+        for name, m, n, t, smp, thr in (
+                ("configs[2] LG d=4 T=200 N=4e6 PG (conditional sweep)", models.lg4(), 4_000_000, 200, _abi.SAMPLER_PG, 0.5),
+                ("configs[3] SV T=500 N=2e6 PGAS (conditional sweep)", models.stochastic_volatility(), 2_000_000, 500,
+                 _abi.SAMPLER_PGAS, 1.0)):
+            try:
+                h = _lib.Handle(_abi.make_config(m, n, t, sampler=smp, ess_threshold=thr, device=local_rank))
+                h.set_observations(rng.normal(size=(t, m.dy)) * 0.3)
+                ms, nl = timed(h, True)
+                out[name] = {"ms_per_sweep": ms, "particle_steps_per_s": n * t / (ms * 1e-3), "launches": nl}
+                h.close()
+            except _lib.ApsError as e:   # e.g. not enough free HBM next to the bench handles
+                out[name] = {"error": str(e)}
+    for kind, nm in ((_abi.RESAMPLE_STRATIFIED, "stratified"), (_abi.RESAMPLE_RESIDUAL, "residual"),
+                     (_abi.RESAMPLE_MULTINOMIAL, "multinomial")):
+        name = f"configs[4] LG d=1 T=100 N={world}e6 SMC {nm}" + (f" sharded over {world} GPUs" if world > 1 else " (1-GPU shard size)")
+        if world == 1:
+            h = _lib.Handle(_abi.make_config(models.linear_gaussian(), N_PARTICLES, T_STEPS, resampler=kind, device=local_rank))
+            h.set_observations(make_data())
+        else:
+            from advancedps_b200 import distributed as D
+            h = D.create_sharded_handle(models.linear_gaussian(), N_PARTICLES * world, T_STEPS, make_data(), resampler=kind,
+                                        device=local_rank)
+        ms, nl = timed(h, False)
+        if world > 1:
+            import torch
+            import torch.distributed as dist
+            tt = torch.tensor([ms], dtype=torch.float64, device="cuda")
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            ms = float(tt.item())
+        out[name] = {"ms_per_sweep": ms, "particle_steps_per_s": world * N_PARTICLES * T_STEPS / (ms * 1e-3), "launches": nl}
+        barrier()
+        h.close()
+    return out
 
 
 def cpu_baseline():
@@ -206,7 +299,8 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU legs (cpu_baseline, oracle_check)")
+    ap.add_argument("--no-configs", action="store_true", help="skip the timing of configs[2..4]")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 0)
 
@@ -279,6 +373,12 @@ def main():
 
     # ---- e2e: the public API with host buffers; H2D of the observations and D2H of the
     #      SMCSample fields (weights + log-evidence) inside the timed region
+    # the parity columns of the line: every ancestor index of the last timed sweep against the oracle
+    # (1 GPU; the handle still holds that sweep), evidence against the oracle at world x 1e6 (N GPUs)
+    parity = None
+    if rank == 0 and not args.no_cpu_baseline:
+        parity = oracle_check(MASTER_SEED + args.steps - 1, logev, world, h if world == 1 else None)
+    barrier()
     rng = np.random.default_rng(MASTER_SEED)
     if world == 1:
         tssm = S.TracedSSM(model, Y)
@@ -325,15 +425,23 @@ def main():
             gbs = alg_bytes[nm] * N_PARTICLES / (avg * 1e-3) / 1e9 if nm in alg_bytes else None
             kern[nm] = {"launches": n, "avg_us": 1e3 * avg, "share": ms / tot_ms, "alg_GBps": gbs}
     dom = max((k for k in kern if k in alg_bytes), key=lambda k: kern[k]["share"])
-    try:  # dram bytes per launch from the committed ncu --set full captures (profiles/)
-        with open(os.path.join(ROOT, "profiles", "ncu_traffic_r01.json")) as f:
+    # dram bytes per launch: NOT measured in this run (that needs ncu); the figures of the committed
+    # `ncu --set full` captures are passed through with their provenance
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
             ncu_traffic = json.load(f)
     except (OSError, ValueError):
         ncu_traffic = {}
+    traffic_src = ncu_traffic.get("source_label", "static: profiles/ncu_traffic.json (ncu capture of an earlier commit), not measured in this run")
+    step_us = 1e3 * dev_ms_max / args.steps / T_STEPS
+    step_gbs = 40 * N_PARTICLES / (step_us * 1e-6) / 1e9
     roofline = {"bound": "hbm", "kernel": dom, "achieved": kern[dom]["alg_GBps"], "peak": peak, "unit": "GB/s",
-                "frac": kern[dom]["alg_GBps"] / peak, "traffic": ncu_traffic.get(dom), "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": alg_bytes[dom] * N_PARTICLES,
-                "note": "N=1e6 per launch is L2-resident and latency-bound; see resample_isolated for the streaming figure",
+                "frac": kern[dom]["alg_GBps"] / peak, "traffic": ncu_traffic.get(dom), "traffic_source": traffic_src,
+                "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes[dom] * N_PARTICLES,
+                "bound_in_this_sweep": "instruction issue / integer + fp64 pipes: N=1e6 per launch is L2-resident, so the HBM "
+                                       "fraction of the in-sweep kernels is a utilisation figure, not their limiter; the HBM-bound "
+                                       "measurement is resample_isolated",
+                "whole_step": {"algorithmic_bytes": 40 * N_PARTICLES, "us": step_us, "achieved": step_gbs, "frac": step_gbs / peak},
                 "kernels": kern}
     # the graded resample kernel in isolation: 2^25 particles (> L2), L2 flushed between launches
     n_iso = 1 << 25
@@ -342,7 +450,7 @@ def main():
         iso = 12 * n_iso / (avg_ms * 1e-3) / 1e9
         roofline["resample_isolated"] = {"n": n_iso, "avg_ms": avg_ms, "min_ms": min_ms, "achieved": iso,
                                          "frac": iso / peak, "algorithmic_bytes_per_launch": 12 * n_iso,
-                                         "traffic": ncu_traffic.get("k_resample_isolated_n2^25"),
+                                         "traffic": ncu_traffic.get("k_resample_isolated_n2^25"), "traffic_source": traffic_src,
                                          "l2": "flushed between launches (512 MB memset, then a 256 MB streaming read so L2 is cold and clean)"}
     barrier()
 
@@ -361,14 +469,26 @@ def main():
             # bit-equal (parity tests, also at this size: tests/test_gpu_full_size.py); against the
             # exact Kalman log-likelihood the difference is the Monte-Carlo error of the filter.
             "logZ": {"estimate": logev, "kalman_exact": kal_ll, "error_vs_kalman": logev - kal_ll,
-                     "vs_oracle": "bit-equal at test sizes (tests/test_gpu_sweep_parity.py); full size: see oracle_check"},
+                     "vs_oracle": "oracle_check: the oracle at this run's full size (evidence; at 1 GPU also every ancestor index)"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "api": ("sampler.sample" if world == 1 else "distributed.sample") + "(rng, TracedSSM(model, Y), SMC(N, resample_systematic)) -> SMCSample(weights, logevidence)"},
             "gpu_launches": launches, "clocks": clk, "roofline": roofline,
         }
+        if parity is not None:
+            out["logZ"]["oracle_check"] = parity
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline()
-            out["logZ"]["oracle_check"] = oracle_check(MASTER_SEED + args.steps - 1, logev)
+    cfgs = None
+    if not args.no_configs:
+        del hp
+        S._handles.clear()
+        if world > 1:
+            D._sharded.clear()
+        barrier()
+        cfgs = config_block(world, rank, local_rank, barrier)
+    if rank == 0:
+        if cfgs is not None:
+            out["configs"] = cfgs
         emit(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

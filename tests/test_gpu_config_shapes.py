@@ -66,17 +66,18 @@ def test_config_shape_two_iterations(name):
 
 @pytest.fixture
 def direct_launches(monkeypatch):
-    """Ranks EMULATED on one GPU spin on each other from different streams of one process, and the
-    queue of pending launches is a shared, bounded resource there: with more than ~1000 launches (or
-    graph nodes) outstanding per rank, a rank that spins at the first exchange keeps the others'
-    kernels from being enqueued at all (observed with the round-1 library as well: residual, 12
-    launches per step, runs at T = 50 and hangs at T = 100). The emulated cases therefore stay below
-    ~1000 launches per rank and launch directly; one process per GPU (tests/mp_sharded_worker.py,
-    bench.py) has no such limit and replays the CUDA graph at the full T."""
+    """Ranks EMULATED on one GPU are host threads of one process whose kernels spin on each other. A
+    sweep is launched asynchronously in full before anything completes; once a rank has more than
+    roughly 600-700 launches outstanding (each carries ~1 KB of kernel parameters) its launching
+    thread blocks inside the driver and keeps the other ranks' first kernels from being enqueued --
+    everybody then waits at the first exchange. Observed with the round-1 library as well (residual,
+    12 launches per step: runs at T = 50, hangs at T = 64). The emulated cases therefore stay below
+    ~550 launches per rank and launch directly; one process per GPU (tests/mp_sharded_worker.py,
+    bench.py) has no such coupling and replays the CUDA graph at the full T."""
     monkeypatch.setenv("APS_NO_GRAPH", "1")
 
 
-@pytest.mark.parametrize("name,world,T_emu", [("c3", 2, 200), ("c3", 8, 200), ("c4", 4, 180), ("c4", 8, 180)])
+@pytest.mark.parametrize("name,world,T_emu", [("c3", 2, 160), ("c3", 8, 160), ("c4", 4, 100), ("c4", 8, 100)])
 def test_config_shape_sharded(name, world, T_emu, direct_launches):
     mk, N, _, smp, thr, dkey = SHAPES[name]
     T = T_emu
@@ -100,9 +101,9 @@ def test_config_shape_sharded(name, world, T_emu, direct_launches):
 @pytest.mark.parametrize("world", [1, 4])
 def test_c5_shape_four_resamplers(res, world, direct_launches):
     """configs[4]: LG d=1, T=100, the resampler sweep; 8192 particles per (emulated) rank. (Emulated
-    residual / multinomial: 10-12 launches per step, so T = 64 -- see `direct_launches`.)"""
+    residual / multinomial: 10-12 launches per step, so T = 40 -- see `direct_launches`.)"""
     m = models.linear_gaussian()
-    T = 100 if world == 1 or res in (_abi.RESAMPLE_SYSTEMATIC, _abi.RESAMPLE_STRATIFIED) else 64
+    T = 100 if world == 1 or res in (_abi.RESAMPLE_SYSTEMATIC, _abi.RESAMPLE_STRATIFIED) else 40
     N = 8192 * world
     _, Y = O.simulate_data(m, T, 0xDA7A0005)
     cfg = _abi.make_config(m, N, T, resampler=res)
