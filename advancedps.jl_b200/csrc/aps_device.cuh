@@ -88,17 +88,22 @@ __host__ __device__ __forceinline__ size_t aps_mailbox_alloc_bytes(long long ste
     return aps_mail_bytes() + aps_fatcnt_bytes(steps) + (size_t)steps * APS_FAT_MAX * sizeof(FatEntry);
 }
 
-// parent of global child slot g if it lies in a deferred range, else -1
-__device__ __forceinline__ int fat_lookup(const FatEntry *ent, int nfat, int g) {
+// parent of global child slot g if it lies in a deferred range, else -1. `ent` is the block's
+// shared-memory copy of the list (fat_stage): the list is read once per block at L2 -- sharded, peers
+// push into it, so neither ld.global.nc nor L1 may serve it -- and looked up from shared memory.
+__device__ __forceinline__ int fat_lookup(const int4 *ent, int nfat, int g) {
     int a = -1;
 #pragma unroll 1
     for (int e = 0; e < nfat; ++e) {
-        // (not __ldg: sharded, peers may still be pushing into later lists while this kernel runs, which
-        // breaks the read-only contract of ld.global.nc; L2 is the coherence point for peer writes)
-        const int4 v = __ldcg(reinterpret_cast<const int4 *>(ent + e));
+        const int4 v = ent[e];
         if (g >= v.x && g < v.y) a = v.z;
     }
     return a;
+}
+// all threads of the block; ends with a block barrier
+__device__ __forceinline__ void fat_stage(int4 *s_ent, const FatEntry *ent, int nfat) {
+    for (int e = threadIdx.x; e < nfat; e += blockDim.x) s_ent[e] = __ldcg(reinterpret_cast<const int4 *>(ent + e));
+    __syncthreads();
 }
 
 __device__ __forceinline__ u64 ld_sys_u64(const u64 *p) {

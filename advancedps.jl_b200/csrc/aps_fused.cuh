@@ -272,14 +272,29 @@ __global__ void __launch_bounds__(APS_FUSED_MAX_THREADS, 1) k_sweep_fused(const 
                 for (int k = 0; k < D; ++k) xref[k] = c.ref[(t - 1) * D + k];   // X_ref[c-1], c = t+1
             }
             const int p_end = (i1 + 1) >> 1;
+            double mx = aps_bits2d(0xFFF0000000000000ULL), pmx = mx;   // running maxima (-inf), encoded once after the loop
+            bool any = false, pany = false;
+            // order inside one iteration: ancestors, Philox rounds (integer only) while they arrive, the
+            // parent-state gather, the floating-point half of the draw while THAT is in flight
             for (int p = (i0 >> 1) + tid; p < p_end; p += NT) {
-                double z[2 * D];
-                aps_pair_normals<D>(key, (u64)((c.slot0 >> 1) + p), (u64)t, z);
                 const int j0 = 2 * p;
                 int2 a2 = make_int2(0, 0);
                 if (t > 1) a2 = *reinterpret_cast<const int2 *>(anc_prev + j0);
                 double2 lw2 = make_double2(0.0, 0.0);
                 if (!reset) lw2 = *reinterpret_cast<const double2 *>(c.logw + j0);
+                uint64_t w[2 * D];
+                aps_pair_words<D>(key, (u64)((c.slot0 >> 1) + p), (u64)t, w);
+                double xg[2][D];
+                if (t > 1) {
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int a = j0 + h < N ? (h ? a2.y : a2.x) : 0;   // (padding slot of an odd N: entry not written)
+#pragma unroll
+                        for (int k = 0; k < D; ++k) xg[h][k] = __ldcg(xp + (long long)k * NS + a);
+                    }
+                }
+                double z[2 * D];
+                aps_words_to_normals<D>(w, z);
                 double xo[2][D];
                 double lwo[2], lpo[2];
 #pragma unroll
@@ -292,35 +307,29 @@ __global__ void __launch_bounds__(APS_FUSED_MAX_THREADS, 1) k_sweep_fused(const 
                     for (int k = 0; k < D; ++k) x[k] = 0.0;
                     if (i < N) {
                         const bool is_ref = has_ref && c.slot0 + i == c.Ng - 1;   // the reference keeps the globally last slot
-                        double xpv[D];
-                        if (t > 1 && (!is_ref || pgas_step)) {
-                            const int a = h ? a2.y : a2.x;
-#pragma unroll
-                            for (int k = 0; k < D; ++k) xpv[k] = __ldcg(xp + (long long)k * NS + a);
-                        }
                         if (is_ref) {
 #pragma unroll
                             for (int k = 0; k < D; ++k) x[k] = c.ref[(t - 1) * D + k];
                         } else if (t == 1) {
                             aps_prior_draw<D>(&c.md, z + h * D, x);
                         } else {
-                            aps_trans_draw<D>(&c.md, xpv, z + h * D, x);
+                            aps_trans_draw<D>(&c.md, xg[h], z + h * D, x);
                         }
                         const double ll = aps_obs_logpdf<D, DY, OBS>(&c.md, x, y);
                         const double lw = (reset ? 0.0 : (h ? lw2.y : lw2.x)) + ll;
                         lwo[h] = lw;
                         if (lw != lw) bad = 1;
                         else {
-                            const u64 e = aps_encode_ordered(lw);
-                            bmax = e > bmax ? e : bmax;
+                            mx = lw > mx ? lw : mx;
+                            any = true;
                         }
                         if (pgas_step) {   // log f(X_ref[c-1] | X_i[c-2]) + logW_i   (src/pgas.jl:26-46)
-                            const double lp = aps_trans_logpdf<D>(&c.md, xpv, xref) + lw;
+                            const double lp = aps_trans_logpdf<D>(&c.md, xg[h], xref) + lw;
                             lpo[h] = lp;
                             if (lp != lp) bad |= 2u;
                             else {
-                                const u64 e = aps_encode_ordered(lp);
-                                pmax = e > pmax ? e : pmax;
+                                pmx = lp > pmx ? lp : pmx;
+                                pany = true;
                             }
                         }
                     }
@@ -333,6 +342,8 @@ __global__ void __launch_bounds__(APS_FUSED_MAX_THREADS, 1) k_sweep_fused(const 
                 *reinterpret_cast<double2 *>(c.logw + j0) = make_double2(lwo[0], lwo[1]);
                 if (pgas_step) *reinterpret_cast<double2 *>(reinterpret_cast<double *>(qp_t) + j0) = make_double2(lpo[0], lpo[1]);
             }
+            if (any) bmax = aps_encode_ordered(mx);
+            if (pany) pmax = aps_encode_ordered(pmx);
             // block maxima: warp shuffles, then one 64-bit shared-memory atomic per warp
             bmax = warp_max_u64(bmax);
             if (lane == 0 && bmax) atomicMax(&s_acc[FA_BMAX], bmax);

@@ -108,6 +108,8 @@ __global__ void APS_K1_BOUNDS k_propagate(const __grid_constant__ DevCtx c, cons
 
     u64 bmax = 0;
     unsigned bad = 0;
+    double mx = aps_bits2d(0xFFF0000000000000ULL);   // running maximum of this thread's log-weights (-inf)
+    bool any = false;
     const long long npairs = (N + 1) >> 1;
     const long long pair0 = c.slot0 >> 1;
     const bool multi = MULTI;
@@ -122,7 +124,8 @@ __global__ void APS_K1_BOUNDS k_propagate(const __grid_constant__ DevCtx c, cons
         int nfat = MULTI ? __ldcg(&c.fat_cnt[t - 1]) : c.fat_cnt[t - 1];   // (sharded: pushed by the peers, read at L2)
         if (!nfat) return;
         if (nfat > APS_FAT_MAX) nfat = APS_FAT_MAX;
-        const FatEntry *fatl = c.fat + (t - 1) * APS_FAT_MAX;
+        __shared__ int4 fatl[APS_FAT_MAX];
+        fat_stage(fatl, c.fat + (t - 1) * APS_FAT_MAX, nfat);   // (nfat is the same in every thread: uniform)
         int32_t *ancw = const_cast<int32_t *>(anc);
 #pragma unroll 1
         for (long long pp = p; pp < npairs; pp += (long long)gridDim.x * APS_K1_THREADS) {
@@ -136,10 +139,10 @@ __global__ void APS_K1_BOUNDS k_propagate(const __grid_constant__ DevCtx c, cons
             }
         }
     };
-    // the normals do not depend on the ancestors (nor, sharded, on the peers): draw the first pair's
+    // the random words do not depend on the ancestors (nor, sharded, on the peers): draw the first pair's
     // before the loads / the wait for the peers
-    double z[2 * D];
-    if (p < npairs) aps_pair_normals<D>(key, (u64)(pair0 + p), (u64)t, z);
+    uint64_t w[2 * D];
+    if (p < npairs) aps_pair_words<D>(key, (u64)(pair0 + p), (u64)t, w);
     if (!MULTI) resolve_fat();
     SpanProbe probe(&c.acc[t], 0, c.dbg & 16);
     // log-weights start at zero in every sweep (src/smc.jl:45-51); afterwards they restart from
@@ -159,14 +162,42 @@ __global__ void APS_K1_BOUNDS k_propagate(const __grid_constant__ DevCtx c, cons
         __syncthreads();
         resolve_fat();  // the peers' pushes into this rank's list are complete now
     }
+    // Order inside one iteration: ancestor indices first (they are needed for the only dependent load
+    // chain of the loop), then the integer-only Philox rounds while they arrive, then the parent-state
+    // gather, then the floating-point half of the draw (log / sqrt / sincospi) while THAT is in flight.
     for (bool first = true; p < npairs; p += (long long)gridDim.x * APS_K1_THREADS, first = false) {
-        if (!first) aps_pair_normals<D>(key, (u64)(pair0 + p), (u64)t, z);
         const long long i0 = 2 * p;
         int2 a2 = make_int2(0, 0);
         if (t > 1) a2 = MULTI ? __ldcg(reinterpret_cast<const int2 *>(anc + i0))   // scattered by the peers: read at L2
                               : *reinterpret_cast<const int2 *>(anc + i0);
         double2 lw2 = make_double2(0.0, 0.0);
         if (!reset) lw2 = *reinterpret_cast<const double2 *>(c.logw + i0);
+        if (!first) aps_pair_words<D>(key, (u64)(pair0 + p), (u64)t, w);
+        double z[2 * D];
+        if (D > 2) aps_words_to_normals<D>(w, z);   // (d >= 3: registers are the limit -- finish the draw before the gather)
+        double xg[2][D];   // parent states of the two slots
+        auto gather = [&](int h) {
+            long long a = h ? a2.y : a2.x;  // global parent index
+            if (i0 + h >= N) a = c.slot0;   // (padding slot of an odd N: its ancestor entry is not written)
+            const double *xsrc = xp;
+            if (multi && !(c.dbg & 4)) {
+                const unsigned al = (unsigned)(a - c.slot0);
+                if (al < (unsigned)N) {
+                    a = al;  // own shard (the common case)
+                } else {     // the parent lives on a peer: read its state over NVLink
+                    const int owner = (int)((unsigned)a / (unsigned)N);
+                    a -= (long long)owner * N;
+                    xsrc = c.peers->x[owner] + xoff;
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < D; ++k) xg[h][k] = xsrc[(long long)k * NS + a];
+        };
+        if (D <= 2 && t > 1) {
+            gather(0);
+            gather(1);
+        }
+        if (D <= 2) aps_words_to_normals<D>(w, z);
         double xo[2][D];
         double lwo[2];
 #pragma unroll
@@ -183,30 +214,16 @@ __global__ void APS_K1_BOUNDS k_propagate(const __grid_constant__ DevCtx c, cons
                 } else if (t == 1) {
                     aps_prior_draw<D>(&c.md, z + h * D, x);
                 } else {
-                    long long a = h ? a2.y : a2.x;  // global parent index
-                    const double *xsrc = xp;
-                    if (multi && !(c.dbg & 4)) {
-                        const unsigned al = (unsigned)(a - c.slot0);
-                        if (al < (unsigned)N) {
-                            a = al;  // own shard (the common case)
-                        } else {     // the parent lives on a peer: read its state over NVLink
-                            const int owner = (int)((unsigned)a / (unsigned)N);
-                            a -= (long long)owner * N;
-                            xsrc = c.peers->x[owner] + xoff;
-                        }
-                    }
-                    double xpv[D];
-#pragma unroll
-                    for (int k = 0; k < D; ++k) xpv[k] = xsrc[(long long)k * NS + a];
-                    aps_trans_draw<D>(&c.md, xpv, z + h * D, x);
+                    if (D > 2) gather(h);
+                    aps_trans_draw<D>(&c.md, xg[h], z + h * D, x);
                 }
                 const double ll = aps_obs_logpdf<D, DY, OBS>(&c.md, x, y);
                 const double lw = (reset ? 0.0 : (h ? lw2.y : lw2.x)) + ll;
                 lwo[h] = lw;
                 if (lw != lw) bad = 1;
                 else {
-                    const u64 e = aps_encode_ordered(lw);
-                    bmax = e > bmax ? e : bmax;
+                    mx = lw > mx ? lw : mx;   // (encoded once per thread after the loop: the encoding is monotone)
+                    any = true;
                 }
             }
 #pragma unroll
@@ -217,6 +234,7 @@ __global__ void APS_K1_BOUNDS k_propagate(const __grid_constant__ DevCtx c, cons
             *reinterpret_cast<double2 *>(xt + (long long)k * NS + i0) = make_double2(xo[0][k], xo[1][k]);
         *reinterpret_cast<double2 *>(c.logw + i0) = make_double2(lwo[0], lwo[1]);
     }
+    if (any) bmax = aps_encode_ordered(mx);
     bmax = block_max_u64<APS_K1_THREADS / 32>(bmax, red);
     bad = __syncthreads_or(bad);
     if (threadIdx.x == 0) {

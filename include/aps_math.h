@@ -67,14 +67,11 @@ APS_HD double aps_sqrt(double x) {
 /* 64x64 -> 128 multiply */
 APS_HD void aps_mul64(uint64_t a, uint64_t b, uint64_t *hi, uint64_t *lo) {
 #if defined(__CUDA_ARCH__)
-    /* one pass over the four 32x32 partial products (4 IMAD.WIDE + carries) instead of separate
-     * mul.hi / mul.lo sequences */
-    const uint32_t a0 = (uint32_t)a, a1 = (uint32_t)(a >> 32), b0 = (uint32_t)b, b1 = (uint32_t)(b >> 32);
-    const uint64_t t0 = (uint64_t)a0 * b0;
-    const uint64_t t1 = (uint64_t)a0 * b1 + (t0 >> 32);
-    const uint64_t t2 = (uint64_t)a1 * b0 + (uint32_t)t1;
-    *lo = (t2 << 32) | (uint32_t)t0;
-    *hi = (uint64_t)a1 * b1 + (t1 >> 32) + (t2 >> 32);
+    /* nvcc's own 64-bit high / low products share their partial products and use carry-in forms
+     * (IMAD.WIDE.U32.X): 11 instructions per Philox round against 16 for a hand-written pass over
+     * the four 32x32 products (cuobjdump, round 2) */
+    *hi = __umul64hi(a, b);
+    *lo = a * b;
 #else
     unsigned __int128 p = (unsigned __int128)a * b;
     *hi = (uint64_t)(p >> 64);
@@ -164,18 +161,8 @@ APS_HD double aps_exp(double x) {
  * x = 2^k m, m in [sqrt(1/2), sqrt(2)); f = m - 1; s = f / (2 + f); log(1+f) = 2 atanh(s)
  * with the classical 7-term minimax polynomial in s^2 (Remez coefficients as published with
  * the Sun/FreeBSD msun e_log.c algorithm).                                                    */
-APS_HD double aps_log(double x) {
-    if (!(x == x)) return x;
-    if (x < 0.0) return aps_bits2d(0x7FF8000000000000ULL);
-    if (x == 0.0) return aps_bits2d(0xFFF0000000000000ULL);
-    uint64_t b = aps_d2bits(x);
-    if (b >= 0x7FF0000000000000ULL) return x; /* +inf */
-    int k = 0;
-    if (b < 0x0010000000000000ULL) { /* subnormal */
-        x = x * 0x1.0p54;
-        b = aps_d2bits(x);
-        k = -54;
-    }
+/* core: b = bits of a positive, finite, NORMAL double; k0 = exponent adjustment already applied */
+APS_HD double aps_log_core(uint64_t b, int k) {
     k += (int)(b >> 52) - 1023;
     uint64_t mant = b & 0x000FFFFFFFFFFFFFULL;
     double m = aps_bits2d(mant | 0x3FF0000000000000ULL); /* [1,2) */
@@ -200,6 +187,22 @@ APS_HD double aps_log(double x) {
     double t = aps_fma(s, hfsq + R, dk * 0x1.a39ef35793c76p-33);
     return aps_fma(dk, 0x1.62e42fee00000p-1, -((hfsq - t) - f));
 }
+APS_HD double aps_log(double x) {
+    if (!(x == x)) return x;
+    if (x < 0.0) return aps_bits2d(0x7FF8000000000000ULL);
+    if (x == 0.0) return aps_bits2d(0xFFF0000000000000ULL);
+    uint64_t b = aps_d2bits(x);
+    if (b >= 0x7FF0000000000000ULL) return x; /* +inf */
+    int k = 0;
+    if (b < 0x0010000000000000ULL) { /* subnormal */
+        x = x * 0x1.0p54;
+        b = aps_d2bits(x);
+        k = -54;
+    }
+    return aps_log_core(b, k);
+}
+/* same value as aps_log(x) for a positive, finite, normal x (no special cases to test) */
+APS_HD double aps_log_normal(double x) { return aps_log_core(aps_d2bits(x), 0); }
 
 /* ------------------------------------------------------------------ sin(pi t), cos(pi t), t in [0, 2]
  * n = round(2t), r = t - n/2 in [-1/4, 1/4] (exact), Taylor in (pi r) with pre-multiplied
@@ -230,12 +233,10 @@ APS_HD void aps_sincospi(double t, double *sp, double *cp) {
     c = aps_fma(c, r2, 4.0587121264167685);
     c = aps_fma(c, r2, -4.934802200544679);
     c = aps_fma(c, r2, 1.0);
-    switch (n & 3) {
-        case 0: *sp = s; *cp = c; break;
-        case 1: *sp = c; *cp = -s; break;
-        case 2: *sp = -s; *cp = -c; break;
-        default: *sp = -c; *cp = s; break;
-    }
+    /* quadrant rotation without branches: odd n swaps the two, the signs follow n (exact) */
+    const double a = (n & 1) ? c : s, b = (n & 1) ? s : c;
+    *sp = (n & 2) ? -a : a;
+    *cp = ((n + 1) & 2) ? -b : b;
 }
 
 /* ------------------------------------------------------------------ standard normals
@@ -244,7 +245,7 @@ APS_HD void aps_sincospi(double t, double *sp, double *cp) {
 APS_HD void aps_normal_pair(uint64_t w0, uint64_t w1, double *z0, double *z1) {
     double u1 = aps_u01_open(w0);
     double t = 2.0 * aps_u01(w1);
-    double rho = aps_sqrt(-2.0 * aps_log(u1));
+    double rho = aps_sqrt(-2.0 * aps_log_normal(u1)); /* u1 in [2^-53, 1): positive and normal */
     double s, c;
     aps_sincospi(t, &s, &c);
     *z0 = rho * c;

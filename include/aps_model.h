@@ -99,6 +99,24 @@ APS_HD void aps_pair_normals(uint64_t key, uint64_t pair, uint64_t step, double 
     }
 }
 
+/* the same draws in two halves, so that a kernel can put its (dependent, long-latency) parent-state
+ * gather between the integer-only Philox rounds and the floating-point transform */
+template <int D>
+APS_HD void aps_pair_words(uint64_t key, uint64_t pair, uint64_t step, uint64_t *w /* 2 D */) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int j = 0; j < D; ++j)
+        aps_philox2x64(pair, aps_ctr1(step, APS_DOM_STATE, (uint32_t)j), key, &w[2 * j], &w[2 * j + 1]);
+}
+template <int D>
+APS_HD void aps_words_to_normals(const uint64_t *w, double *z /* 2 D */) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int j = 0; j < D; ++j) aps_normal_pair(w[2 * j], w[2 * j + 1], &z[2 * j], &z[2 * j + 1]);
+}
+
 /* x_1 = mu0 + sigma0 z   (src/pgas.jl:60-62: simulate(rng, prior)) */
 template <int D>
 APS_HD void aps_prior_draw(const aps_model_dev *md, const double *z, double *x) {
