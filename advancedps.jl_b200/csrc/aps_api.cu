@@ -250,6 +250,8 @@ struct aps_handle {
     FusedArgs fa;
     int fused_grid, fused_threads, fused_smem;
     bool last_fused, fused_forced;
+    int grid_prop;   // grid of the propagate kernel (propagate_grid), computed on first use
+    bool pdl;        // programmatic dependent launch between the three kernels of a step (single GPU, systematic / stratified, SMC / PG)
     // stepwise container (aps_pc_*): reweights done so far, decision points settled so far
     bool pc_active;
     long long pc_t, pc_decided;
@@ -436,6 +438,9 @@ extern "C" int aps_create(const aps_config *cfg, aps_handle **out) {
     prefer_max_smem(h->f_pmax);
     prefer_max_smem(h->f_psel);
     // ---- fused persistent sweep: one CTA per SM, every CTA owns a contiguous chunk of slots
+    // PDL: only where a step is exactly K1 -> K2 -> K3 (every kernel of the chain carries the wait)
+    h->pdl = world == 1 && (cfg->resampler == APS_RESAMPLE_SYSTEMATIC || cfg->resampler == APS_RESAMPLE_STRATIFIED) &&
+             cfg->sampler != APS_PGAS && getenv("APS_PDL") != nullptr && atoi(getenv("APS_PDL")) != 0;
     h->f_fused = nullptr;
     h->fused_forced = getenv("APS_FUSED") != nullptr && atoi(getenv("APS_FUSED")) != 0;
     if (world == 1 && getenv("APS_NO_FUSED") == nullptr) {
@@ -544,19 +549,58 @@ struct Launcher {
         L.end();              \
     } while (0)
 
+// launch with the programmatic-stream-serialization attribute (PDL): the kernel may begin while the
+// previous kernel of the stream drains; see APS_PDL_WAIT in csrc/aps_device.cuh
+template <typename... KArgs, typename... Args>
+static void launch_pdl(void (*fn)(KArgs...), int grid, int block, size_t smem, cudaStream_t st, bool pdl, Args... args) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3((unsigned)block);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, fn, KArgs(args)...);
+}
+
 static double *x_slab_of(const DevCtx &c, long long t) { return c.x + ((t - 1 + c.x_slabs) % c.x_slabs) * (long long)c.d * c.NS; }
 static int32_t *anc_slab_of(const DevCtx &c, long long sidx) { return c.anc + ((sidx + c.anc_slabs) % c.anc_slabs) * c.NS; }
 
+// Grid of the propagate kernel: one thread per slot pair, grid-stride. The grid is (a) no larger than
+// what is resident at once (occupancy x SMs: a second wave of a few blocks would double the kernel's
+// tail) and (b) sized so that every thread runs the SAME number of iterations: with npairs / resident
+// threads = 2.64 (N = 1e6) a maximal grid leaves a third of the blocks idle for the last third of
+// the kernel; ceil(npairs / (iterations x threads)) blocks spread the same work evenly.
+static int propagate_grid(aps_handle *h, long long n_local) {
+    const long long npairs = (n_local + 1) / 2;
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, h->f_prop, APS_K1_THREADS, 0) != cudaSuccess || occ < 1) {
+        cudaGetLastError();
+        occ = 1;
+    }
+#ifdef APS_K1_GRID_PER_SM   // tuning experiments
+    if (occ > APS_K1_GRID_PER_SM) occ = APS_K1_GRID_PER_SM;
+#endif
+    const long long resident = (long long)occ * sm_count() * APS_K1_THREADS;
+    long long iters = (npairs + resident - 1) / resident;
+    if (const char *e = getenv("APS_K1_ITERS")) {   // tuning experiments (single GPU only: sharded grids must be resident)
+        if (h->ctx.world == 1 && atoll(e) > 0) iters = atoll(e);
+    }
+    long long g = (npairs + iters * APS_K1_THREADS - 1) / (iters * APS_K1_THREADS);
+    if (g < 1) g = 1;
+    return (int)g;
+}
+
 static void launch_propagate(aps_handle *h, const DevCtx &c, long long t, Launcher &L) {
     cudaStream_t st = h->stream;
-    // one thread per slot pair, grid-stride over at most 5 resident blocks per SM
-    long long gk1l = ((c.N + 1) / 2 + APS_K1_THREADS - 1) / APS_K1_THREADS;
-#ifndef APS_K1_GRID_PER_SM
-#define APS_K1_GRID_PER_SM 5
-#endif
-    if (gk1l > (long long)sm_count() * APS_K1_GRID_PER_SM) gk1l = (long long)sm_count() * APS_K1_GRID_PER_SM;
+    if (h->grid_prop == 0) h->grid_prop = propagate_grid(h, c.N);
     // slab addressing is resolved here, once per launch (no 64-bit modulo in the kernels)
-    APS_LAUNCH(0, h->f_prop<<<(int)gk1l, APS_K1_THREADS, 0, st>>>(c, t, x_slab_of(c, t), x_slab_of(c, t - 1), anc_slab_of(c, t - 1)));
+    APS_LAUNCH(0, launch_pdl(h->f_prop, h->grid_prop, APS_K1_THREADS, 0, st, h->pdl && t > 1, c, (long long)t, x_slab_of(c, t),
+                             (const double *)x_slab_of(c, t - 1), (const int32_t *)anc_slab_of(c, t - 1)));
 }
 
 static void launch_decision(aps_handle *h, const DevCtx &c, long long t, res_fn f_res, Launcher &L) {
@@ -564,7 +608,7 @@ static void launch_decision(aps_handle *h, const DevCtx &c, long long t, res_fn 
     const int gp = stride_grid(c.N);
     const int gt = (int)c.num_tiles;
     if (c.resampler == APS_RESAMPLE_SYSTEMATIC || c.resampler == APS_RESAMPLE_STRATIFIED) {
-        APS_LAUNCH(2, f_res<<<gt, APS_K3_THREADS, APS_K3_DYN_SMEM, st>>>(c, t, anc_slab_of(c, t), h->tmap_q));
+        APS_LAUNCH(2, launch_pdl(f_res, gt, APS_K3_THREADS, APS_K3_DYN_SMEM, st, h->pdl, c, (long long)t, anc_slab_of(c, t), h->tmap_q));
     } else {
         const bool multi = c.world > 1;
         MultiArgs a;
@@ -651,7 +695,7 @@ static long long enqueue_sweep(aps_handle *h, LaunchProf *prof = nullptr) {
     const int gt = (int)c.num_tiles;
     for (long long t = 1; t <= c.T; ++t) {
         launch_propagate(h, c, t, L);
-        APS_LAUNCH(1, k_normalise<IN_LOGW><<<gt, APS_K2_THREADS, 0, st>>>(c, c.logw, t));
+        APS_LAUNCH(1, launch_pdl(k_normalise<IN_LOGW>, gt, APS_K2_THREADS, 0, st, h->pdl, c, (const double *)c.logw, (long long)t));
         launch_decision(h, c, t, h->f_res, L);
     }
     launch_fill_fat(h, c, c.T, L);
@@ -752,16 +796,22 @@ static int sweep_impl(aps_handle *h, uint64_t master_seed, const double *ref_tra
                                                : "aps_sweep: a peer rank did not answer within the exchange timeout")
                                       : "aps_sweep: particle weights could not be normalised (all -Inf or NaN log-weights)");
     *logevidence = h->h_st->logev;
-    if (c.dbg & 16) {
+    if (c.dbg & 16) {   // in-graph timeline of the three kernels (globaltimer: first block start -> last block end), us per step
         std::vector<StepAcc> acc((size_t)c.T + 2);
         cudaMemcpy(acc.data(), c.acc, sizeof(StepAcc) * acc.size(), cudaMemcpyDeviceToHost);
-        double span = 0, gap = 0;
-        for (long long t = 1; t <= c.T; ++t) {
-            span += (double)(acc[t].t_last[0] - ~acc[t].t_first_neg[0]);
-            if (t > 1) gap += (double)(~acc[t].t_first_neg[0] - acc[t - 1].t_last[0]);
+        double span[3] = {0, 0, 0}, gap[3] = {0, 0, 0};
+        long long cnt = 0;
+        for (long long t = 2; t <= c.T; ++t) {
+            const double b0 = (double)~acc[t].t_first_neg[0], e0 = (double)acc[t].t_last[0];
+            const double b1 = (double)~acc[t].t_first_neg[1], e1 = (double)acc[t].t_last[1];
+            const double b2 = (double)~acc[t].t_first_neg[2], e2 = (double)acc[t].t_last[2];
+            const double e2p = (double)acc[t - 1].t_last[2];
+            span[0] += e0 - b0; span[1] += e1 - b1; span[2] += e2 - b2;
+            gap[0] += b0 - e2p; gap[1] += b1 - e0; gap[2] += b2 - e1;
+            ++cnt;
         }
-        fprintf(stderr, "[aps rank %d] k_propagate first-block-start -> last-block-end: %.2f us avg; end(t-1) -> start(t): %.2f us avg\n",
-                c.rank, span / c.T * 1e-3, gap / (c.T - 1) * 1e-3);
+        fprintf(stderr, "[aps rank %d] per step (us): gap %.2f | K1 %.2f | gap %.2f | K2 %.2f | gap %.2f | K3 %.2f  (first block start -> last block end)\n",
+                c.rank, gap[0] / cnt * 1e-3, span[0] / cnt * 1e-3, gap[1] / cnt * 1e-3, span[1] / cnt * 1e-3, gap[2] / cnt * 1e-3, span[2] / cnt * 1e-3);
     }
     if (fused && (c.dbg & 32)) {   // per-phase time of every CTA (ns, summed over the sweep): min / median / max over the CTAs
         std::vector<u64> d((size_t)h->fused_grid * 8);

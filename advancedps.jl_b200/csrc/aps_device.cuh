@@ -40,7 +40,22 @@ typedef unsigned long long u64;
 #ifndef APS_K3_MINBLOCKS
 #define APS_K3_MINBLOCKS 8
 #endif
-#define APS_K1_THREADS 256      // threads per block of the grid-stride kernels (propagate, maxima)
+// 128 threads x 8 blocks per SM (64 registers): measured best at N = 1e6 (2.64 ms per sweep; 256 x 4: 2.74,
+// 128 x 10 at 48 registers: 2.72, 256 x 5 at 48 registers: 2.84 -- scratch/time_k1.py, round 2)
+#ifndef APS_K1_THREADS
+#define APS_K1_THREADS 128      // threads per block of the grid-stride kernels (propagate, maxima)
+#endif
+#ifndef APS_K1_MINBLOCKS
+#define APS_K1_MINBLOCKS 8
+#endif
+// Programmatic dependent launch (single-GPU graph of the systematic / stratified path): a kernel
+// launched with the programmatic-serialization attribute may start while its predecessor drains;
+// it must not touch anything the predecessor reads or writes before APS_PDL_WAIT() returns (the
+// predecessor is then complete and flushed). APS_PDL_TRIGGER() at the top of a kernel lets ITS
+// successor launch as soon as every block of this kernel is resident. Both are no-ops in a kernel
+// launched without the attribute.
+#define APS_PDL_WAIT() asm volatile("griddepcontrol.wait;" ::: "memory")
+#define APS_PDL_TRIGGER() asm volatile("griddepcontrol.launch_dependents;" ::: "memory")
 
 // ---------------------------------------------------------------- multi-GPU sharding (one process per GPU)
 // Rank r owns the contiguous global slots [r Nl, (r+1) Nl). Peers' state / ancestor stores and a

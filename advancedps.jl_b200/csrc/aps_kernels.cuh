@@ -91,16 +91,13 @@ __global__ void k_init_sweep(const __grid_constant__ DevCtx c) {
 // One thread per PAIR of adjacent slots (2p, 2p+1): the pair shares D Philox blocks and their
 // Box-Muller normals (aps_pair_normals), ancestors / log-weights / states move as 8- and 16-byte
 // vectors. Block maxima of the new log-weights are folded into one atomicMax per block.
-#ifdef APS_K1_MINBLOCKS   // tuning experiments only (csrc/build.sh -DAPS_K1_MINBLOCKS=6); the default leaves it to ptxas
 #define APS_K1_BOUNDS __launch_bounds__(APS_K1_THREADS, APS_K1_MINBLOCKS)
-#else
-#define APS_K1_BOUNDS __launch_bounds__(APS_K1_THREADS)
-#endif
 template <int D, int DY, int OBS, bool MULTI>
 __global__ void APS_K1_BOUNDS k_propagate(const __grid_constant__ DevCtx c, const long long t,
                                                            double *__restrict__ xt, const double *__restrict__ xp,
                                                            const int32_t *anc) {  // not __restrict__: patched below
     __shared__ u64 red[APS_K1_THREADS / 32];
+    if (c.dbg & 512) APS_PDL_TRIGGER();
     const long long N = c.N, NS = c.NS;
     const int has_ref = c.sp->has_ref;   // (sweep parameters: written before the graph is launched)
     const u64 key = c.sp->key;
@@ -143,6 +140,7 @@ __global__ void APS_K1_BOUNDS k_propagate(const __grid_constant__ DevCtx c, cons
     // before the loads / the wait for the peers
     uint64_t w[2 * D];
     if (p < npairs) aps_pair_words<D>(key, (u64)(pair0 + p), (u64)t, w);
+    APS_PDL_WAIT();   // everything below reads or writes what the previous kernels of the sweep produce
     if (!MULTI) resolve_fat();
     SpanProbe probe(&c.acc[t], 0, c.dbg & 16);
     // log-weights start at zero in every sweep (src/smc.jl:45-51); afterwards they restart from
@@ -172,13 +170,14 @@ __global__ void APS_K1_BOUNDS k_propagate(const __grid_constant__ DevCtx c, cons
                               : *reinterpret_cast<const int2 *>(anc + i0);
         double2 lw2 = make_double2(0.0, 0.0);
         if (!reset) lw2 = *reinterpret_cast<const double2 *>(c.logw + i0);
-        if (!first) aps_pair_words<D>(key, (u64)(pair0 + p), (u64)t, w);
+        if (!first && !(c.dbg & 64)) aps_pair_words<D>(key, (u64)(pair0 + p), (u64)t, w);   // (dbg 64 / 128 / 256: ablations, timing only)
         double z[2 * D];
         if (D > 2) aps_words_to_normals<D>(w, z);   // (d >= 3: registers are the limit -- finish the draw before the gather)
         double xg[2][D];   // parent states of the two slots
         auto gather = [&](int h) {
             long long a = h ? a2.y : a2.x;  // global parent index
             if (i0 + h >= N) a = c.slot0;   // (padding slot of an odd N: its ancestor entry is not written)
+            if (c.dbg & 128) a = c.slot0 + i0 + h;
             const double *xsrc = xp;
             if (multi && !(c.dbg & 4)) {
                 const unsigned al = (unsigned)(a - c.slot0);
@@ -197,7 +196,14 @@ __global__ void APS_K1_BOUNDS k_propagate(const __grid_constant__ DevCtx c, cons
             gather(0);
             gather(1);
         }
-        if (D <= 2) aps_words_to_normals<D>(w, z);
+        if (D <= 2) {
+            if (c.dbg & 256) {
+#pragma unroll
+                for (int k = 0; k < 2 * D; ++k) z[k] = (double)(w[k] >> 40) * 0x1.0p-24 - 0.5;
+            } else {
+                aps_words_to_normals<D>(w, z);
+            }
+        }
         double xo[2][D];
         double lwo[2];
 #pragma unroll
@@ -235,6 +241,7 @@ __global__ void APS_K1_BOUNDS k_propagate(const __grid_constant__ DevCtx c, cons
         *reinterpret_cast<double2 *>(c.logw + i0) = make_double2(lwo[0], lwo[1]);
     }
     if (any) bmax = aps_encode_ordered(mx);
+    if (!(c.dbg & 512)) APS_PDL_TRIGGER();   // this block's stores are issued: the next kernel may start launching
     bmax = block_max_u64<APS_K1_THREADS / 32>(bmax, red);
     bad = __syncthreads_or(bad);
     if (threadIdx.x == 0) {
@@ -375,9 +382,12 @@ __global__ void __launch_bounds__(APS_K2_THREADS) k_normalise(const __grid_const
     __shared__ u64 red[APS_K2_WARPS];
     __shared__ u64 s_tot[3];
     __shared__ unsigned s_last;
+    if (c.dbg & 512) APS_PDL_TRIGGER();
     const long long N = c.N;
     const long long base = (long long)blockIdx.x * APS_TILE;
     StepAcc *acc = &c.acc[s];
+    APS_PDL_WAIT();
+    SpanProbe probe(acc, 1, c.dbg & 16);
     if (threadIdx.x < 3) s_tot[threadIdx.x] = 0;
     __syncthreads();
     u64 max_enc = acc->max_enc;
@@ -432,6 +442,7 @@ __global__ void __launch_bounds__(APS_K2_THREADS) k_normalise(const __grid_const
             s2 += qs * qs;
         }
     }
+    if (!(c.dbg & 512)) APS_PDL_TRIGGER();
     // tile totals: warp shuffles, then one shared-memory integer atomic per warp and total
     // (exact integers, so the order is irrelevant; cheaper than three block-wide reductions)
     s0 = warp_sum_u64(s0);
@@ -456,6 +467,7 @@ __global__ void __launch_bounds__(APS_K2_THREADS) k_normalise(const __grid_const
             acc->tot[3] = max_enc;
             acc->pad1 = (acc->bad | bad_in) ? 1u : 0u;
         }
+        probe.end();
         return;
     }
     if (threadIdx.x == 0) {
@@ -864,9 +876,13 @@ __global__ void __launch_bounds__(APS_K3_THREADS, MULTI ? APS_K3_MINBLOCKS - 2 :
     __shared__ __align__(8) uint64_t mbar;
     unsigned char *tilebuf = dynsmem;
     int *own = reinterpret_cast<int *>(dynsmem + APS_TILE_BYTES);
+    if (c.dbg & 512) APS_PDL_TRIGGER();
     const long long N = c.N;
     const StepPlan *pp = c.plan + s;
     const int tid = threadIdx.x;
+    if (DEFER && !MULTI) zero_own<APS_K3_THREADS, APS_K3_CPT>(own);   // (shared memory only: before the wait)
+    APS_PDL_WAIT();
+    SpanProbe probe(&c.acc[s], 2, c.dbg & 16);
     const long long base = (long long)blockIdx.x * APS_TILE;
     AncDst dst;
     dst.base = anc_out;
@@ -918,7 +934,7 @@ __global__ void __launch_bounds__(APS_K3_THREADS, MULTI ? APS_K3_MINBLOCKS - 2 :
     u64 tprefix = 0;
     if (!defer) tprefix = c.tile_prefix[blockIdx.x];
 
-    zero_own<APS_K3_THREADS, APS_K3_CPT>(own);
+    if (!(DEFER && !MULTI)) zero_own<APS_K3_THREADS, APS_K3_CPT>(own);
     if (defer) {
         // Deferred plan (see k_normalise): while the TMA load is in flight, sum the tile totals
         // (integers: any order), take the part below this tile as its prefix, and derive the plan of
@@ -1062,6 +1078,7 @@ __global__ void __launch_bounds__(APS_K3_THREADS, MULTI ? APS_K3_MINBLOCKS - 2 :
     }
     excl += tprefix;
 
+    if (!(c.dbg & 512)) APS_PDL_TRIGGER();
     // ---- child range of the tile and of this thread (every thread evaluates the three bounds itself)
     const bool first_tile = blockIdx.x == 0 && c.slot0 == 0;  // K(C_{-1}) := 0 for the globally first parent
     bool unsafe = false;
@@ -1110,6 +1127,7 @@ __global__ void __launch_bounds__(APS_K3_THREADS, MULTI ? APS_K3_MINBLOCKS - 2 :
 
     // reference particle keeps the last slot (src/container.jl:219-224); PGAS may overwrite it
     if (blockIdx.x == gridDim.x - 1 && tid == 0 && n < c.Ng && c.rank == c.world - 1) anc_out[N - 1] = (int32_t)(c.Ng - 1);
+    probe.end();
 }
 
 // ---------------------------------------------------------------- multinomial / residual resampling
