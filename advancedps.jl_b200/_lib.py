@@ -20,7 +20,7 @@ _HDR = [os.path.join(_HERE, "..", "include", f) for f in ("aps_b200.h", "aps_mod
 EXPORTS = [
     "aps_create", "aps_destroy", "aps_set_observations", "aps_sweep", "aps_sweep_profiled",
     "aps_pick_trajectory",
-    "aps_get_weights", "aps_get_weights_view", "aps_get_logweights", "aps_get_final_states", "aps_get_trajectory",
+    "aps_host_alloc", "aps_host_free", "aps_get_weights", "aps_get_weights_view", "aps_get_logweights", "aps_get_final_states", "aps_get_trajectory",
     "aps_get_trajectories", "aps_pc_begin", "aps_pc_resample_propagate", "aps_pc_reweight", "aps_pc_logz",
     "aps_set_logweights",
     "aps_get_step_stats", "aps_get_states", "aps_get_ancestors", "aps_get_fat_counts", "aps_smoothing_mean", "aps_last_sweep_ms",
@@ -79,6 +79,44 @@ def check(rc):
 
 def ptr(a):
     return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+class _PinnedPool:
+    """Page-locked host buffers for owned results (``aps_host_alloc``). A buffer belongs to the numpy
+    array handed out until that array is garbage-collected, then it is reused: in steady state
+    ``sample()`` returns an owned weights vector without a page-locking call or a staging copy."""
+
+    def __init__(self, keep=4):
+        self.free, self.keep = {}, keep
+
+    def array(self, n, dtype=np.float64):
+        import weakref
+
+        nbytes = int(n) * np.dtype(dtype).itemsize
+        lst = self.free.get(nbytes)
+        if lst:
+            p = lst.pop()
+        else:
+            p = C.c_void_p()
+            check(lib().aps_host_alloc(C.c_int64(nbytes), C.byref(p)))
+            p = p.value
+        buf = (C.c_char * nbytes).from_address(p)
+        a = np.frombuffer(buf, dtype=dtype, count=int(n))
+        weakref.finalize(buf, self._give_back, nbytes, p)   # `a` keeps `buf` alive through its base
+        return a
+
+    def _give_back(self, nbytes, p):
+        lst = self.free.setdefault(nbytes, [])
+        if len(lst) < self.keep:
+            lst.append(p)
+        else:
+            try:
+                lib().aps_host_free(C.c_void_p(p))
+            except Exception:
+                pass
+
+
+_pinned = _PinnedPool()
 
 
 class Handle:
@@ -155,8 +193,10 @@ class Handle:
         check(lib().aps_pick_trajectory(self._h, ptr(traj), C.byref(slot)))
         return slot.value, traj
 
-    def weights(self):
-        w = np.empty(self.N)
+    def weights(self, pinned=False):
+        """Normalised weights of this handle's slots, an owned array. ``pinned=True`` takes the buffer
+        from the page-locked pool (DMA-speed copy; the buffer returns to the pool when the array dies)."""
+        w = _pinned.array(self.N) if pinned else np.empty(self.N)
         check(lib().aps_get_weights(self._h, ptr(w)))
         return w
 

@@ -1055,6 +1055,18 @@ static int final_resampled(aps_handle *h, int *out) {
     return APS_OK;
 }
 
+extern "C" int aps_host_alloc(int64_t bytes, void **out) {
+    if (!out || bytes <= 0) return fail(APS_ERR_INVALID, "aps_host_alloc: bad argument");
+    *out = nullptr;
+    CU(cudaMallocHost(out, (size_t)bytes));
+    return APS_OK;
+}
+
+extern "C" int aps_host_free(void *p) {
+    if (p) CU(cudaFreeHost(p));
+    return APS_OK;
+}
+
 extern "C" int aps_get_weights(aps_handle *h, double *w_out) {
     NEED_SWEEP("aps_get_weights");
     if (!w_out) return fail(APS_ERR_INVALID, "aps_get_weights: null output");

@@ -16,7 +16,9 @@
 typedef unsigned long long u64;
 
 #define APS_THREADS 128         // threads per block of the tile kernels (normalise, resample, select)
+#ifndef APS_IPT
 #define APS_IPT 16              // items per thread in a tile: 16 u64 = one 128-byte row of the TMA box
+#endif
 #define APS_TILE (APS_THREADS * APS_IPT)   // 2048 particles per tile
 #define APS_CPT 20              // child slots per thread in one expand pass
 #define APS_CAP (APS_THREADS * APS_CPT)    // 2560 children staged per pass

@@ -170,14 +170,13 @@ __global__ void APS_K1_BOUNDS k_propagate(const __grid_constant__ DevCtx c, cons
                               : *reinterpret_cast<const int2 *>(anc + i0);
         double2 lw2 = make_double2(0.0, 0.0);
         if (!reset) lw2 = *reinterpret_cast<const double2 *>(c.logw + i0);
-        if (!first && !(c.dbg & 64)) aps_pair_words<D>(key, (u64)(pair0 + p), (u64)t, w);   // (dbg 64 / 128 / 256: ablations, timing only)
+        if (!first) aps_pair_words<D>(key, (u64)(pair0 + p), (u64)t, w);
         double z[2 * D];
         if (D > 2) aps_words_to_normals<D>(w, z);   // (d >= 3: registers are the limit -- finish the draw before the gather)
         double xg[2][D];   // parent states of the two slots
         auto gather = [&](int h) {
             long long a = h ? a2.y : a2.x;  // global parent index
             if (i0 + h >= N) a = c.slot0;   // (padding slot of an odd N: its ancestor entry is not written)
-            if (c.dbg & 128) a = c.slot0 + i0 + h;
             const double *xsrc = xp;
             if (multi && !(c.dbg & 4)) {
                 const unsigned al = (unsigned)(a - c.slot0);
@@ -196,14 +195,7 @@ __global__ void APS_K1_BOUNDS k_propagate(const __grid_constant__ DevCtx c, cons
             gather(0);
             gather(1);
         }
-        if (D <= 2) {
-            if (c.dbg & 256) {
-#pragma unroll
-                for (int k = 0; k < 2 * D; ++k) z[k] = (double)(w[k] >> 40) * 0x1.0p-24 - 0.5;
-            } else {
-                aps_words_to_normals<D>(w, z);
-            }
-        }
+        if (D <= 2) aps_words_to_normals<D>(w, z);
         double xo[2][D];
         double lwo[2];
 #pragma unroll

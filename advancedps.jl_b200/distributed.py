@@ -94,7 +94,7 @@ def sample(rng, model, sampler, n_iter=None, group=None):
     if isinstance(sampler, S.SMC):
         h = _sharded_handle(model, sampler, group)
         logev = h.sweep(_shared_key(rng, group))
-        return S.SMCSample(h, model, h.weights(), logev)
+        return S.SMCSample(h, model, h.weights(pinned=True), logev)
     if n_iter is None:
         raise TypeError("sample(rng, model, PG|PGAS, n_iter): n_iter is required")
     out, state = [], None

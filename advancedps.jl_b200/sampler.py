@@ -260,7 +260,7 @@ def sample(rng, model, sampler, n_iter=None, materialize=False, **kwargs):
         h = _handle_for(model, sampler)
         logev = h.sweep(_draw_key(rng))
         # weights: an owned copy, as upstream returns (src/smc.jl:56)
-        return SMCSample(h, model, h.weights(), logev, materialize=materialize)
+        return SMCSample(h, model, h.weights(pinned=True), logev, materialize=materialize)
     if n_iter is None:
         raise TypeError("sample(rng, model, PG|PGAS, n_iter): n_iter is required")
     out, state = [], None

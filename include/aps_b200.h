@@ -97,6 +97,13 @@ int aps_sweep_profiled(aps_handle *h, uint64_t master_seed, const double *ref_tr
 int aps_pick_trajectory(aps_handle *h, double *traj_out, int64_t *index_out);
 /* (sharded handles: a collective call; index_out is the GLOBAL slot, every rank gets the trajectory) */
 
+/* Page-locked host buffers for results the caller wants to OWN (SMCSample.weights is an owned
+ * Vector upstream, src/smc.jl:56): a device-to-host copy into such a buffer runs at DMA speed
+ * (no staging pass), and unlike aps_get_weights_view the buffer belongs to the caller until
+ * aps_host_free. The Python mirror recycles them through a small pool.                          */
+int aps_host_alloc(int64_t bytes, void **out);
+int aps_host_free(void *p);
+
 /* SMCSample fields (src/smc.jl:23-27,56) materialised lazily.                                  */
 int aps_get_weights(aps_handle *h, double *w_out /* N */);                 /* getweights, container.jl:95 */
 /* same weights without a staging copy: *w_out points to a pinned host buffer owned by the handle

@@ -158,14 +158,37 @@ function handle_for(model::DeviceSSM, sampler; device::Integer=0)
     k, thr = kind_thr(sampler.resampler)
     key = (sampler_id(sampler), sampler.nparticles, k, thr, device)
     cached = get(HANDLES, model, nothing)
-    if cached !== nothing && cached[1] == key
-        return cached[2]
+    # isequal, not ==: a bare resampler carries thr = NaN, and NaN == NaN is false -- `==` would build
+    # a new device handle (tens of GB) on every call and leave the old one to a finalizer the GC has
+    # no reason to run (it does not see device memory)
+    if cached !== nothing && isequal(cached[1], key)
+        h = cached[2]
+        set_observations!(h, model.Y)                        # the caller may have changed model.Y in place
+        return h
     end
+    for (_, (_, old)) in HANDLES                             # release device memory NOW, not at some GC
+        destroy!(old)
+    end
+    empty!(HANDLES)
     cfg = ApsConfig(model.model, sampler.nparticles, size(model.Y, 1), key[1], k, thr, 1, device, 0, 1)
     h = Handle(cfg, model.Y)
-    empty!(HANDLES)
     HANDLES[model] = (key, h)
     return h
+end
+
+function set_observations!(h::Handle, Y::Matrix{Float64})
+    Yt = permutedims(Y)                                      # dy x T column-major == T x dy row-major
+    GC.@preserve Yt check(ccall((:aps_set_observations, lib), Cint,
+                                (Ptr{Cvoid}, Ptr{Float64}, Int64, Int64), h.ptr, Yt, size(Y, 1), size(Y, 2)))
+    return h
+end
+
+function destroy!(h::Handle)
+    if h.ptr != C_NULL
+        ccall((:aps_destroy, lib), Cint, (Ptr{Cvoid},), h.ptr)
+        h.ptr = C_NULL
+    end
+    return nothing
 end
 
 function sweep!(h::Handle, seed::UInt64, ref::Union{Nothing,Matrix{Float64}}; ref_on_device::Bool=false)
@@ -194,6 +217,46 @@ function Base.getindex(t::LazyTrajectories, i::Int)
     traj = Matrix{Float64}(undef, t.h.d, t.h.T)
     check(ccall((:aps_get_trajectory, lib), Cint, (Ptr{Cvoid}, Int64, Ptr{Float64}), t.h.ptr, i - 1, traj))
     return AdvancedPS.Trace(DeviceSSM(t.model.model, t.model.Y, permutedims(traj)), AdvancedPS.TracedRNG())
+end
+
+# collect(pc) of SMCSample (src/smc.jl:56): every trajectory in one call (T x N x d on the device side)
+function Base.collect(t::LazyTrajectories)
+    X = Array{Float64,3}(undef, t.h.d, t.h.n, t.h.T)          # d x N x T column-major == T x N x d row-major
+    check(ccall((:aps_get_trajectories, lib), Cint, (Ptr{Cvoid}, Ptr{Float64}), t.h.ptr, X))
+    return [AdvancedPS.Trace(DeviceSSM(t.model.model, t.model.Y, permutedims(X[:, i, :])), AdvancedPS.TracedRNG())
+            for i in 1:t.h.n]
+end
+
+# ------------------------------------------------------------------ the device container, call by call
+# (src/container.jl:171-363 as single calls: what test/container.jl and test/pgas.jl:61-91 drive)
+struct DeviceContainer
+    h::Handle
+end
+function DeviceContainer(rng::Random.AbstractRNG, model::DeviceSSM, sampler, ref::Union{Nothing,Matrix{Float64}}=nothing)
+    h = handle_for(model, sampler)
+    rt = ref === nothing ? nothing : permutedims(ref)
+    GC.@preserve rt check(ccall((:aps_pc_begin, lib), Cint, (Ptr{Cvoid}, UInt64, Ptr{Float64}),
+                                h.ptr, rand(rng, UInt64), rt === nothing ? C_NULL : pointer(rt)))
+    return DeviceContainer(h)
+end
+function AdvancedPS.reweight!(pc::DeviceContainer, ref=nothing)
+    done = Ref{Int32}(0)
+    check(ccall((:aps_pc_reweight, lib), Cint, (Ptr{Cvoid}, Ref{Int32}), pc.h.ptr, done))
+    return done[] != 0
+end
+function AdvancedPS.resample_propagate!(rng, pc::DeviceContainer, sampler, resampler, ref=nothing)
+    res = Ref{Int32}(0)
+    check(ccall((:aps_pc_resample_propagate, lib), Cint, (Ptr{Cvoid}, Ref{Int32}), pc.h.ptr, res))
+    return pc
+end
+function AdvancedPS.logZ(pc::DeviceContainer)
+    z = Ref{Float64}()
+    check(ccall((:aps_pc_logz, lib), Cint, (Ptr{Cvoid}, Ref{Float64}), pc.h.ptr, z))
+    return z[]
+end
+function set_logweights!(pc::DeviceContainer, logWs::Vector{Float64})      # pc.logWs = v (test/pgas.jl:82)
+    check(ccall((:aps_set_logweights, lib), Cint, (Ptr{Cvoid}, Ptr{Float64}), pc.h.ptr, logWs))
+    return pc
 end
 
 # ------------------------------------------------------------------ AbstractMCMC.sample for SMC (src/smc.jl:35-57)
