@@ -183,6 +183,7 @@ static void preload_kernels() {
     cudaFuncGetAttributes(&a, k_smooth_step);
     cudaFuncGetAttributes(&a, k_traj_step);
     cudaFuncGetAttributes(&a, k_pc_provisional);
+    cudaFuncGetAttributes(&a, k_route_barrier);
     cudaGetLastError();
     done = true;
 }
@@ -293,6 +294,7 @@ static void free_handle(aps_handle *h) {
     for (int i = 0; i < h->n_ipc_opened; ++i) cudaIpcCloseMemHandle(h->ipc_opened[i]);
     cudaFree(h->d_mail);
     cudaFree(h->d_peers);
+    cudaFree(h->ctx.rank_woff);
     cudaFree(h->fa.ex_max);
     cudaFree(h->fa.ex_pmax);
     cudaFree(h->fa.ex_tot);
@@ -390,8 +392,15 @@ extern "C" int aps_create(const aps_config *cfg, aps_handle **out) {
     CUH(cudaMalloc(&h->d_scratch, sizeof(double) * (size_t)Nl * d));
     // mailbox + fat-parent lists in one allocation (one IPC handle covers both)
     c.fat_steps = T + 2;
-    CUH(cudaMalloc(&h->d_mail, aps_mailbox_alloc_bytes(c.fat_steps)));
-    CUH(cudaMemset(h->d_mail, 0, aps_mailbox_alloc_bytes(c.fat_steps)));
+    // sharded multinomial / residual: receive buffer of the routed draws (worst case: every draw lands here)
+    const bool iid = cfg->resampler == APS_RESAMPLE_MULTINOMIAL || cfg->resampler == APS_RESAMPLE_RESIDUAL;
+    c.recv_cap = (world > 1 && iid) ? N : 0;
+    CUH(cudaMalloc(&h->d_mail, aps_mailbox_alloc_bytes(c.fat_steps, c.recv_cap)));
+    CUH(cudaMemset(h->d_mail, 0, aps_recv_off(c.fat_steps)));
+    c.recv_cnt = reinterpret_cast<unsigned long long *>(reinterpret_cast<char *>(h->d_mail) + aps_recvcnt_off(c.fat_steps));
+    c.recv = reinterpret_cast<u64 *>(reinterpret_cast<char *>(h->d_mail) + aps_recv_off(c.fat_steps));
+    c.rank_woff = nullptr;
+    if (c.recv_cap) CUH(cudaMalloc(&c.rank_woff, sizeof(u64) * (size_t)c.fat_steps * (APS_MAX_RANKS + 1)));
     c.fat_cnt = reinterpret_cast<int *>(reinterpret_cast<char *>(h->d_mail) + aps_mail_bytes());
     c.fat = reinterpret_cast<FatEntry *>(reinterpret_cast<char *>(h->d_mail) + aps_mail_bytes() + aps_fatcnt_bytes(c.fat_steps));
     c.fat_min = fat_min_for(N);
@@ -653,9 +662,17 @@ static void launch_decision(aps_handle *h, const DevCtx &c, long long t, res_fn 
             if (multi) APS_LAUNCH(2, k_residual_exchange<1><<<1, 32, 0, st>>>(c, t, c.plan + t, h->d_rs + t, c.plan + c.T + 1));
         }
         APS_LAUNCH(2, k_cumsum<<<gt, APS_THREADS, 0, st>>>(a));
-        // sharded: every rank makes all Ng draws and keeps those in its own weight range
-        const int gs = stride_grid((c.Ng + 1) / 2);
-        APS_LAUNCH(2, k_multi_search<1><<<gs, APS_K1_THREADS, 0, st>>>(a, &h->d_sp->key));
+        if (multi && c.recv_cap && getenv("APS_NO_ROUTE") == nullptr) {
+            // sharded: every rank makes 1/G of the draws and routes each to the rank that owns its weight range
+            const int gr = stride_grid(((c.Ng + 1) / 2 + c.world - 1) / c.world);
+            APS_LAUNCH(2, k_multi_route<<<gr, APS_K1_THREADS, 0, st>>>(a, &h->d_sp->key, c, t));
+            APS_LAUNCH(2, k_route_barrier<<<1, 32, 0, st>>>(c, t, c.plan + t));
+            APS_LAUNCH(2, k_multi_search_recv<<<stride_grid(c.N), APS_K1_THREADS, 0, st>>>(a, c, t));
+        } else {
+            // (single GPU; or APS_NO_ROUTE: every rank makes all Ng draws and keeps those in its own weight range)
+            const int gs = stride_grid((c.Ng + 1) / 2);
+            APS_LAUNCH(2, k_multi_search<1><<<gs, APS_K1_THREADS, 0, st>>>(a, &h->d_sp->key));
+        }
         APS_LAUNCH(2, k_tile_counts<<<gt, APS_THREADS, 0, st>>>(a));
         APS_LAUNCH(2, k_scan_tile_counts<<<1, APS_THREADS, 0, st>>>(a, nullptr, c, t));
         APS_LAUNCH(2, k_expand_counts<<<gt, APS_THREADS, 0, st>>>(a, anc_slab_of(c, t), 1, c, t));
@@ -678,6 +695,7 @@ static void reset_sweep_scratch(aps_handle *h) {
     cudaStream_t st = h->stream;
     cudaMemsetAsync(c.acc, 0, sizeof(StepAcc) * (size_t)(c.T + 2), st);
     cudaMemsetAsync(c.fat_cnt, 0, sizeof(int) * (size_t)c.fat_steps, st);
+    if (c.recv_cap) cudaMemsetAsync(c.recv_cnt, 0, sizeof(unsigned long long) * (size_t)c.fat_steps, st);
     if (h->d_rs) {
         cudaMemsetAsync(h->d_rs, 0, sizeof(ResidualState) * (size_t)(c.T + 2), st);
         cudaMemsetAsync(h->d_done2, 0, sizeof(unsigned) * (size_t)(c.T + 2), st);

@@ -72,9 +72,10 @@ typedef unsigned long long u64;
 //   kind 6  PGAS: maximum of the ancestor log-weights         (k_pgas_select)
 //   kind 7  PGAS: ancestor-weight totals per rank             (last block of k_pgas_select)
 //   kind 8  final pick: candidate slot per rank               (k_pick)
+//   kind 9  multinomial / residual: barrier after the draws were routed to their owners (k_route_barrier)
 // All combined quantities are integers, so every rank derives the identical plan.
 #define APS_MAX_RANKS 8
-#define APS_MAIL_KINDS 9
+#define APS_MAIL_KINDS 10
 struct MailSlot {
     ulonglong2 pair[4];   // .x = value, .y = sequence number (epoch * stride + step + 1)
 };
@@ -101,8 +102,16 @@ struct FatEntry {
 // byte layout of the mailbox allocation: MailSlot[KINDS * RANKS] | int fat_cnt[steps] | FatEntry[steps][APS_FAT_MAX]
 __host__ __device__ __forceinline__ size_t aps_mail_bytes() { return sizeof(MailSlot) * APS_MAIL_KINDS * APS_MAX_RANKS; }
 __host__ __device__ __forceinline__ size_t aps_fatcnt_bytes(long long steps) { return ((size_t)steps * sizeof(int) + 15) & ~(size_t)15; }
-__host__ __device__ __forceinline__ size_t aps_mailbox_alloc_bytes(long long steps) {
+__host__ __device__ __forceinline__ size_t aps_recvcnt_off(long long steps) {
     return aps_mail_bytes() + aps_fatcnt_bytes(steps) + (size_t)steps * APS_FAT_MAX * sizeof(FatEntry);
+}
+// Sharded multinomial / residual: the i.i.d. draws are made once (rank r makes draws [r n/G, (r+1) n/G))
+// and ROUTED to the rank whose weight range they fall into -- appended to that rank's receive
+// buffer with a peer atomic (warp-aggregated) and a peer store -- instead of every rank making all
+// n G draws and keeping its own. Layout behind the fat lists: recv_cnt[steps] u64 | recv[recv_cap] u64.
+__host__ __device__ __forceinline__ size_t aps_recv_off(long long steps) { return aps_recvcnt_off(steps) + (((size_t)steps * 8 + 15) & ~(size_t)15); }
+__host__ __device__ __forceinline__ size_t aps_mailbox_alloc_bytes(long long steps, long long recv_cap) {
+    return aps_recv_off(steps) + (size_t)recv_cap * 8;
 }
 
 // parent of global child slot g if it lies in a deferred range, else -1. `ent` is the block's
@@ -185,7 +194,7 @@ __device__ __forceinline__ void mail_post(const PeerTable *pt, int rank, int wor
     const int r = threadIdx.x;
     if (r < world) {
         MailSlot *dst = pt->mail[r] + kind * APS_MAX_RANKS + rank;
-        if (kind == 2 || APS_STRICT_FENCES)
+        if (kind == 2 || kind == 9 || APS_STRICT_FENCES)   // 2 and 9 publish data written with plain peer stores
             for (int k = 0; k < nv; ++k) st_pair_sys_release(&dst->pair[k], v[k], seq);
         else
             for (int k = 0; k < nv; ++k) st_pair_sys(&dst->pair[k], v[k], seq);

@@ -55,6 +55,11 @@ struct DevCtx {
     FatEntry *fat;         // [steps][APS_FAT_MAX]
     long long fat_steps;   // steps the lists are sized for (T + 2; 1 at the operator level)
     int fat_min, pad3;     // children from which a parent is deferred to the consumer
+    // sharded multinomial / residual: receive buffer of routed draws (peer-mapped, behind the fat lists)
+    unsigned long long *recv_cnt;  // [fat_steps] draws received at each decision point
+    u64 *recv;                     // [recv_cap] their positions, relative to this rank's weight range
+    long long recv_cap;
+    u64 *rank_woff;                // [fat_steps][APS_MAX_RANKS + 1] exclusive weight prefix of the ranks for the draws of a step
     long long n_override;  // operator level: number of indices to draw (0: N, or N-1 with a reference)
     long long ctr_offset;  // operator level: Philox step counter = plan index + ctr_offset
 };
@@ -558,6 +563,14 @@ __global__ void __launch_bounds__(32) k_plan_multi(const __grid_constant__ DevCt
         multi_plan(c, s, s_t, ok, &p, &off);
         c.acc[s].rank_off = off;
         record_plan(c, s, p);
+        if (c.rank_woff) {   // weight prefix of every rank: where a routed multinomial draw belongs
+            u64 run = 0;
+            for (int r = 0; r < c.world; ++r) {
+                c.rank_woff[s * (APS_MAX_RANKS + 1) + r] = run;
+                run += s_t[r][0];
+            }
+            c.rank_woff[s * (APS_MAX_RANKS + 1) + c.world] = run;
+        }
     }
 }
 
@@ -1200,6 +1213,27 @@ __global__ void __launch_bounds__(APS_THREADS) k_cumsum(const __grid_constant__ 
     }
 }
 
+// parent of a draw at position tau of this rank's weight range: two-level search (tile prefix, then
+// the tile's cut-point table brackets a binary search of a few elements)
+__device__ __forceinline__ long long multi_find(const MultiArgs &a, u64 tau) {
+    long long lo = 0, hi = a.num_tiles - 1;
+    while (lo < hi) {
+        const long long mid = (lo + hi + 1) >> 1;
+        if (a.tile_prefix[mid] <= tau) lo = mid;
+        else hi = mid - 1;
+    }
+    const long long tile = lo;
+    const u64 trel = tau - a.tile_prefix[tile];
+    const unsigned short *cp = a.cut + tile * APS_CUT + (long long)(trel >> a.cut_sh[tile]);
+    long long jl = tile * APS_TILE + cp[0], jh = tile * APS_TILE + cp[1];
+    while (jl < jh) {
+        const long long mid = (jl + jh) >> 1;
+        if (a.cum[mid] > tau) jh = mid;
+        else jl = mid + 1;
+    }
+    return jl;
+}
+
 // i.i.d. draws: draw i is word (i & 1) of Philox block i >> 1, so one thread makes two draws; each
 // is a two-level binary search (tile prefix, then the tile's cumulative sums)
 template <int TO_COUNTS>
@@ -1221,24 +1255,7 @@ __global__ void __launch_bounds__(APS_K1_THREADS) k_multi_search(const __grid_co
             const long long i = 2 * p + h;
             const u64 tau = floor_uq53(aps_u53(w[h]), Q) - lo_w;  // relative to this rank's weight range
             if (i >= nd || tau >= len_w) continue;                // (unsigned: also rejects tau below the range)
-            // last tile whose exclusive prefix is <= tau
-            long long lo = 0, hi = a.num_tiles - 1;
-            while (lo < hi) {
-                const long long mid = (lo + hi + 1) >> 1;
-                if (a.tile_prefix[mid] <= tau) lo = mid;
-                else hi = mid - 1;
-            }
-            const long long tile = lo;
-            // first j of the tile with cum[j] > tau: the cut points of tau's bucket and of the next
-            // one bracket it (usually a handful of elements), binary search inside the bracket
-            const u64 trel = tau - a.tile_prefix[tile];
-            const unsigned short *cp = a.cut + tile * APS_CUT + (long long)(trel >> a.cut_sh[tile]);
-            long long jl = tile * APS_TILE + cp[0], jh = tile * APS_TILE + cp[1];
-            while (jl < jh) {
-                const long long mid = (jl + jh) >> 1;
-                if (a.cum[mid] > tau) jh = mid;
-                else jl = mid + 1;
-            }
+            const long long jl = multi_find(a, tau);
             if (TO_COUNTS) {
                 // integer histogram of the offspring counts. (Per-tile totals are NOT accumulated here:
                 // the 489 tile counters share 16 cache lines, and 10^6 atomics on them serialised in
@@ -1248,6 +1265,84 @@ __global__ void __launch_bounds__(APS_K1_THREADS) k_multi_search(const __grid_co
                 a.out32[off + i] = (int32_t)jl;
             }
         }
+    }
+}
+
+// Sharded: rank r makes the draws of the Philox blocks [r pp, (r+1) pp) (pp = ceil(ceil(nd / 2) / G)) and
+// appends each draw's position -- relative to the OWNER's weight range -- to the owner's receive
+// buffer: one peer atomic per warp and owner reserves the slots, peer stores fill them.
+__global__ void __launch_bounds__(APS_K1_THREADS) k_multi_route(const __grid_constant__ MultiArgs a, const u64 *keyp,
+                                                               const __grid_constant__ DevCtx c, const long long s) {
+    if (!a.plan->resampled || a.plan->err) return;
+    const long long nd = *a.n_draws;
+    if (nd <= 0) return;
+    const u64 Q = a.wplan->Q;
+    const u64 key = *keyp;
+    const long long npairs = (nd + 1) >> 1;
+    const long long pp = (npairs + c.world - 1) / c.world;
+    const long long p0 = (long long)c.rank * pp, p1 = p0 + pp < npairs ? p0 + pp : npairs;
+    const u64 *woff = c.rank_woff + s * (APS_MAX_RANKS + 1);
+    u64 off[APS_MAX_RANKS + 1];
+#pragma unroll
+    for (int r = 0; r <= APS_MAX_RANKS; ++r) off[r] = r <= c.world ? woff[r] : ~0ull;
+    const size_t cnt_off = aps_recvcnt_off(c.fat_steps) + (size_t)s * 8, buf_off = aps_recv_off(c.fat_steps);
+    const unsigned lane = threadIdx.x & 31u;
+    const long long span = p1 > p0 ? p1 - p0 : 0;
+    const long long rounds = (span + (long long)gridDim.x * APS_K1_THREADS - 1) / ((long long)gridDim.x * APS_K1_THREADS);
+    for (long long it = 0; it < rounds; ++it) {   // uniform trip count: the warp votes below need every lane
+        const long long p = p0 + it * (long long)gridDim.x * APS_K1_THREADS + (long long)blockIdx.x * APS_K1_THREADS + threadIdx.x;
+        uint64_t w[2] = {0, 0};
+        if (p < p1) aps_philox2x64((u64)p, aps_ctr1((u64)a.step, APS_DOM_RESAMPLE, 0), key, &w[0], &w[1]);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const long long i = 2 * p + h;
+            const bool live = p < p1 && i < nd;
+            u64 tau = 0;
+            int owner = -1;
+            if (live) {
+                tau = floor_uq53(aps_u53(w[h]), Q);
+#pragma unroll
+                for (int r = 0; r < APS_MAX_RANKS; ++r)
+                    if (r < c.world && tau >= off[r] && tau < off[r + 1]) owner = r;
+            }
+            for (int o = 0; o < c.world; ++o) {
+                const unsigned m = __ballot_sync(0xffffffffu, owner == o);
+                if (!m) continue;
+                char *mb = reinterpret_cast<char *>(c.peers->mail[o]);
+                unsigned long long base = 0;
+                if (lane == (unsigned)(__ffs(m) - 1))
+                    base = atomicAdd_system(reinterpret_cast<unsigned long long *>(mb + cnt_off), (unsigned long long)__popc(m));
+                base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+                if (owner == o) {
+                    const unsigned long long pos = base + __popc(m & ((1u << lane) - 1u));
+                    if ((long long)pos < c.recv_cap) reinterpret_cast<u64 *>(mb + buf_off)[pos] = tau - off[o];
+                    else c.st->err = APS_ERR_INVALID;
+                }
+            }
+        }
+    }
+}
+
+// all ranks: the routed draws (plain peer stores + peer atomics of k_multi_route, which is complete on
+// this rank by stream order) are published with a release post; returns when every rank has done so
+__global__ void __launch_bounds__(32) k_route_barrier(const __grid_constant__ DevCtx c, const long long s, const StepPlan *plan) {
+    __shared__ u64 s_v[1];
+    __shared__ u64 s_t[APS_MAX_RANKS][4];
+    if (!plan->resampled || plan->err) return;   // identical on every rank
+    if (threadIdx.x == 0) s_v[0] = 0;
+    const bool ok = block_exchange(c, 9, step_seq(c, s), s_v, 1, s_t);
+    if (!ok && threadIdx.x == 0) c.st->err = APS_ERR_COMM;
+}
+
+// owner side: the draws this rank received, histogrammed into the offspring counts of their parents
+__global__ void __launch_bounds__(APS_K1_THREADS) k_multi_search_recv(const __grid_constant__ MultiArgs a,
+                                                                     const __grid_constant__ DevCtx c, const long long s) {
+    if (!a.plan->resampled || a.plan->err) return;
+    long long n = (long long)__ldcg(c.recv_cnt + s);
+    if (n > c.recv_cap) n = c.recv_cap;
+    for (long long k = (long long)blockIdx.x * APS_K1_THREADS + threadIdx.x; k < n; k += (long long)gridDim.x * APS_K1_THREADS) {
+        const u64 tau = __ldcg(c.recv + k);
+        atomicAdd(&a.counts[multi_find(a, tau)], 1);
     }
 }
 
@@ -1480,6 +1575,14 @@ __global__ void __launch_bounds__(32) k_residual_exchange(const __grid_constant_
             wplan->Q = tot;
             rs->q_off = off;
             if (tot == 0) c.st->err = APS_ERR_WEIGHTS;
+            if (c.rank_woff) {   // the residual draws are routed by the residual-weight prefix of the ranks
+                u64 run = 0;
+                for (int r = 0; r < c.world; ++r) {
+                    c.rank_woff[s * (APS_MAX_RANKS + 1) + r] = run;
+                    run += s_t[r][0];
+                }
+                c.rank_woff[s * (APS_MAX_RANKS + 1) + c.world] = run;
+            }
         }
         if (!ok) c.st->err = APS_ERR_COMM;
     }

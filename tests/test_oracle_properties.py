@@ -69,3 +69,28 @@ def test_degenerate_inputs(kind):
         O.resample(kind, np.zeros(4), 4, key=3)                # "sample could not be selected" (:120,169)
     with pytest.raises(O.OracleError):
         O.resample(kind, np.array([0.5, np.nan]), 2, key=3)
+
+
+def test_canon_truncation_bias_is_bounded_by_n_over_2_pow_s():
+    """q = floor(exp(logw - M) 2^S) truncates; every particle loses < 1 unit of 2^-S of the
+    maximum, so Q (hence every logZ increment) is biased DOWN by at most N 2^-S relative:
+    2^-22 at N = 2^20 (S = 42). Worst case: one dominant particle, all others just below one unit."""
+    N = 1 << 20
+    S = O.weight_shift(N)
+    assert S == 62 - 20
+    lw = np.full(N, np.log(0.999 * 2.0 ** -S))      # each truncates to 0
+    lw[12345] = 0.0
+    seq, canon = O.logsumexp(lw, O.SEQ), O.logsumexp(lw, O.CANON)
+    assert canon == 0.0                              # only the dominant particle survives quantisation
+    bound = np.log1p(N * 2.0 ** -S)
+    assert 0.0 <= seq - canon <= bound and seq - canon > 0.9 * bound   # the bound is attained, not exceeded
+    # typical heavy-tailed weights stay far inside it
+    rng = np.random.default_rng(0)
+    lw = -np.abs(rng.standard_cauchy(N)) * 3.0
+    d = O.logsumexp(lw, O.SEQ) - O.logsumexp(lw, O.CANON)
+    assert -1e-12 <= d <= bound
+    # the ESS sums run on q >> h with h chosen so that sum (q >> h)^2 fits 63 bits: (63 - log2 N) / 2 = 21
+    # bits per weight at N = 2^20, i.e. an ESS accurate to ~1e-6 relative here -- a threshold decision
+    # (ess <= thr N) within that distance of the boundary can differ from the reference's fp64 value
+    assert O.ess(lw, O.CANON) == pytest.approx(O.ess(lw, O.SEQ), rel=1e-5)
+    assert abs(O.ess(lw, O.CANON) / O.ess(lw, O.SEQ) - 1) > 1e-8   # (and it is not accidentally exact)
