@@ -1270,9 +1270,15 @@ __global__ void __launch_bounds__(APS_K1_THREADS) k_multi_search(const __grid_co
 
 // Sharded: rank r makes the draws of the Philox blocks [r pp, (r+1) pp) (pp = ceil(ceil(nd / 2) / G)) and
 // appends each draw's position -- relative to the OWNER's weight range -- to the owner's receive
-// buffer: one peer atomic per warp and owner reserves the slots, peer stores fill them.
+// buffer. Peer atomics are expensive (an NVLink round trip each), so a block reserves its slots with
+// ONE peer atomic per owner: pass 1 counts the block's draws per owner in shared memory, `world`
+// threads reserve the ranges, pass 2 recomputes the draws (Philox is cheaper than a second round of
+// remote traffic) and fills the slots with peer stores. (First version: one peer atomic per warp,
+// owner and iteration -- 18.5 ms per 2-GPU multinomial sweep against 11.2 ms with replicated draws.)
 __global__ void __launch_bounds__(APS_K1_THREADS) k_multi_route(const __grid_constant__ MultiArgs a, const u64 *keyp,
                                                                const __grid_constant__ DevCtx c, const long long s) {
+    __shared__ unsigned s_cnt[APS_MAX_RANKS];
+    __shared__ unsigned long long s_base[APS_MAX_RANKS];
     if (!a.plan->resampled || a.plan->err) return;
     const long long nd = *a.n_draws;
     if (nd <= 0) return;
@@ -1286,38 +1292,47 @@ __global__ void __launch_bounds__(APS_K1_THREADS) k_multi_route(const __grid_con
 #pragma unroll
     for (int r = 0; r <= APS_MAX_RANKS; ++r) off[r] = r <= c.world ? woff[r] : ~0ull;
     const size_t cnt_off = aps_recvcnt_off(c.fat_steps) + (size_t)s * 8, buf_off = aps_recv_off(c.fat_steps);
-    const unsigned lane = threadIdx.x & 31u;
-    const long long span = p1 > p0 ? p1 - p0 : 0;
-    const long long rounds = (span + (long long)gridDim.x * APS_K1_THREADS - 1) / ((long long)gridDim.x * APS_K1_THREADS);
-    for (long long it = 0; it < rounds; ++it) {   // uniform trip count: the warp votes below need every lane
-        const long long p = p0 + it * (long long)gridDim.x * APS_K1_THREADS + (long long)blockIdx.x * APS_K1_THREADS + threadIdx.x;
-        uint64_t w[2] = {0, 0};
-        if (p < p1) aps_philox2x64((u64)p, aps_ctr1((u64)a.step, APS_DOM_RESAMPLE, 0), key, &w[0], &w[1]);
+    if (threadIdx.x < APS_MAX_RANKS) s_cnt[threadIdx.x] = 0;
+    __syncthreads();
+    const long long stride = (long long)gridDim.x * APS_K1_THREADS;
+    const long long first = p0 + (long long)blockIdx.x * APS_K1_THREADS + threadIdx.x;
+    auto owner_of = [&](u64 tau) {
+        int o = 0;
+#pragma unroll
+        for (int r = 1; r < APS_MAX_RANKS; ++r)
+            if (r < c.world && tau >= off[r]) o = r;
+        return o;
+    };
+    // pass 1: how many of this block's draws go to each owner
+    for (long long p = first; p < p1; p += stride) {
+        uint64_t w[2];
+        aps_philox2x64((u64)p, aps_ctr1((u64)a.step, APS_DOM_RESAMPLE, 0), key, &w[0], &w[1]);
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+            if (2 * p + h < nd) atomicAdd(&s_cnt[owner_of(floor_uq53(aps_u53(w[h]), Q))], 1u);
+    }
+    __syncthreads();
+    // one peer atomic per owner reserves this block's slots in the owner's receive buffer
+    if (threadIdx.x < c.world) {
+        const unsigned n = s_cnt[threadIdx.x];
+        char *mb = reinterpret_cast<char *>(c.peers->mail[threadIdx.x]);
+        s_base[threadIdx.x] = n ? atomicAdd_system(reinterpret_cast<unsigned long long *>(mb + cnt_off), (unsigned long long)n) : 0ull;
+        s_cnt[threadIdx.x] = 0;   // becomes the running offset inside the reserved range
+    }
+    __syncthreads();
+    // pass 2: the same draws again, each stored at its reserved slot
+    for (long long p = first; p < p1; p += stride) {
+        uint64_t w[2];
+        aps_philox2x64((u64)p, aps_ctr1((u64)a.step, APS_DOM_RESAMPLE, 0), key, &w[0], &w[1]);
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-            const long long i = 2 * p + h;
-            const bool live = p < p1 && i < nd;
-            u64 tau = 0;
-            int owner = -1;
-            if (live) {
-                tau = floor_uq53(aps_u53(w[h]), Q);
-#pragma unroll
-                for (int r = 0; r < APS_MAX_RANKS; ++r)
-                    if (r < c.world && tau >= off[r] && tau < off[r + 1]) owner = r;
-            }
-            for (int o = 0; o < c.world; ++o) {
-                const unsigned m = __ballot_sync(0xffffffffu, owner == o);
-                if (!m) continue;
+            if (2 * p + h < nd) {
+                const u64 tau = floor_uq53(aps_u53(w[h]), Q);
+                const int o = owner_of(tau);
+                const unsigned long long pos = s_base[o] + atomicAdd(&s_cnt[o], 1u);
                 char *mb = reinterpret_cast<char *>(c.peers->mail[o]);
-                unsigned long long base = 0;
-                if (lane == (unsigned)(__ffs(m) - 1))
-                    base = atomicAdd_system(reinterpret_cast<unsigned long long *>(mb + cnt_off), (unsigned long long)__popc(m));
-                base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
-                if (owner == o) {
-                    const unsigned long long pos = base + __popc(m & ((1u << lane) - 1u));
-                    if ((long long)pos < c.recv_cap) reinterpret_cast<u64 *>(mb + buf_off)[pos] = tau - off[o];
-                    else c.st->err = APS_ERR_INVALID;
-                }
+                if ((long long)pos < c.recv_cap) reinterpret_cast<u64 *>(mb + buf_off)[pos] = tau - off[o];
+                else c.st->err = APS_ERR_INVALID;
             }
         }
     }
