@@ -47,13 +47,23 @@ static prop_fn prop_for_dy(int dy) {
         default: return k_propagate<D, 4, OBS, MULTI>;
     }
 }
+// d = 4: one thread per slot (k_propagate1); APS_K1_PAIRS=1 selects the pair kernel for comparison
+template <int OBS, bool MULTI>
+static prop_fn prop1_for_dy4(int dy) {
+    switch (dy) {
+        case 1: return k_propagate1<4, 1, OBS, MULTI>;
+        case 2: return k_propagate1<4, 2, OBS, MULTI>;
+        case 3: return k_propagate1<4, 3, OBS, MULTI>;
+        default: return k_propagate1<4, 4, OBS, MULTI>;
+    }
+}
 template <int OBS, bool MULTI>
 static prop_fn prop_for_dim(int d, int dy) {
     switch (d) {
         case 1: return prop_for_dy<1, OBS, MULTI>(dy);
         case 2: return prop_for_dy<2, OBS, MULTI>(dy);
         case 3: return prop_for_dy<3, OBS, MULTI>(dy);
-        default: return prop_for_dy<4, OBS, MULTI>(dy);
+        default: return getenv("APS_K1_PAIRS") ? prop_for_dy<4, OBS, MULTI>(dy) : prop1_for_dy4<OBS, MULTI>(dy);
     }
 }
 template <bool MULTI>
@@ -66,7 +76,7 @@ static prop_fn pick_propagate_m(int obs, int d, int dy) {
                 case 1: return k_propagate<1, 1, APS_OBS_CONST, MULTI>;
                 case 2: return k_propagate<2, 1, APS_OBS_CONST, MULTI>;
                 case 3: return k_propagate<3, 1, APS_OBS_CONST, MULTI>;
-                default: return k_propagate<4, 1, APS_OBS_CONST, MULTI>;
+                default: return k_propagate1<4, 1, APS_OBS_CONST, MULTI>;
             }
     }
 }
@@ -252,6 +262,7 @@ struct aps_handle {
     int fused_grid, fused_threads, fused_smem;
     bool last_fused, fused_forced;
     int grid_prop;   // grid of the propagate kernel (propagate_grid), computed on first use
+    bool prop_per_slot;   // k_propagate1 (d = 4): one thread per slot
     bool pdl;        // programmatic dependent launch between the three kernels of a step (single GPU, systematic / stratified, SMC / PG)
     // stepwise container (aps_pc_*): reweights done so far, decision points settled so far
     bool pc_active;
@@ -440,6 +451,7 @@ extern "C" int aps_create(const aps_config *cfg, aps_handle **out) {
     c.ref = h->d_ref;
     c.sp = h->d_sp;
     h->f_prop = pick_propagate(cfg->model.obs_kind, d, cfg->model.dy, world > 1);
+    h->prop_per_slot = d == 4 && getenv("APS_K1_PAIRS") == nullptr;
     prefer_max_smem(h->f_prop);
     h->f_res = pick_resample(cfg->resampler, world > 1, c.defer_plan != 0);
     h->f_pmax = pick_pgas_max(d);
@@ -585,7 +597,8 @@ static int32_t *anc_slab_of(const DevCtx &c, long long sidx) { return c.anc + ((
 // threads = 2.64 (N = 1e6) a maximal grid leaves a third of the blocks idle for the last third of
 // the kernel; ceil(npairs / (iterations x threads)) blocks spread the same work evenly.
 static int propagate_grid(aps_handle *h, long long n_local) {
-    const long long npairs = (n_local + 1) / 2;
+    // work items: slot pairs, or slots for the one-thread-per-slot kernel of d = 4
+    const long long npairs = h->prop_per_slot ? n_local : (n_local + 1) / 2;
     int occ = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, h->f_prop, APS_K1_THREADS, 0) != cudaSuccess || occ < 1) {
         cudaGetLastError();

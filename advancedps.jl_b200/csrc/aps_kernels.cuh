@@ -265,6 +265,134 @@ __global__ void APS_K1_BOUNDS k_propagate(const __grid_constant__ DevCtx c, cons
     probe.end();
 }
 
+// K1 for even state dimensions >= 4: one thread per SLOT. A pair of slots consumes D Philox blocks,
+// slot 2p the normals of blocks 0..D/2-1 and slot 2p+1 those of blocks D/2..D-1 (aps_pair_normals), so
+// with an even D each slot can draw its own D/2 blocks -- same draws, no shared block -- and a
+// thread carries one particle's state instead of two: about half the registers of the pair kernel
+// (d = 4: 128 -> 2 blocks of 256 threads per SM in round 1), twice the resident threads.
+#ifndef APS_K1P_MINBLOCKS
+#define APS_K1P_MINBLOCKS 6
+#endif
+template <int D, int DY, int OBS, bool MULTI>
+__global__ void __launch_bounds__(APS_K1_THREADS, APS_K1P_MINBLOCKS) k_propagate1(const __grid_constant__ DevCtx c, const long long t,
+                                                                                 double *__restrict__ xt, const double *__restrict__ xp,
+                                                                                 const int32_t *anc) {  // not __restrict__: patched below
+    static_assert(D % 2 == 0, "one thread per slot needs an even number of Philox blocks per pair");
+    __shared__ u64 red[APS_K1_THREADS / 32];
+    const long long N = c.N, NS = c.NS;
+    const int has_ref = c.sp->has_ref;
+    const u64 key = c.sp->key;
+    const double *__restrict__ y = c.Y + (t - 1) * c.dy;
+    u64 bmax = 0;
+    unsigned bad = 0;
+    double mx = aps_bits2d(0xFFF0000000000000ULL);
+    bool any = false;
+    const bool multi = MULTI;
+    const u64 seq0 = multi ? c.sp->epoch * (u64)(c.T + 2) : 0ull;
+    const long long xoff = xp - c.x;
+    const long long stride = (long long)gridDim.x * APS_K1_THREADS;
+    long long i = (long long)blockIdx.x * APS_K1_THREADS + threadIdx.x;
+    auto resolve_fat = [&]() {
+        if (t <= 1) return;
+        int nfat = MULTI ? __ldcg(&c.fat_cnt[t - 1]) : c.fat_cnt[t - 1];
+        if (!nfat) return;
+        if (nfat > APS_FAT_MAX) nfat = APS_FAT_MAX;
+        __shared__ int4 fatl[APS_FAT_MAX];
+        fat_stage(fatl, c.fat + (t - 1) * APS_FAT_MAX, nfat);
+        int32_t *ancw = const_cast<int32_t *>(anc);
+#pragma unroll 1
+        for (long long ii = i; ii < N; ii += stride) {
+            const int af = fat_lookup(fatl, nfat, (int)(c.slot0 + ii));
+            if (af >= 0) ancw[ii] = af;
+        }
+    };
+    // this slot's D/2 Philox blocks: counter (pair, ctr1(t, DOM_STATE, half * D/2 + j))
+    auto draw_words = [&](long long slot, uint64_t *w) {
+        const u64 g = (u64)(c.slot0 + slot);
+#pragma unroll
+        for (int j = 0; j < D / 2; ++j)
+            aps_philox2x64(g >> 1, aps_ctr1((u64)t, APS_DOM_STATE, (uint32_t)((g & 1) * (D / 2) + j)), key, &w[2 * j], &w[2 * j + 1]);
+    };
+    uint64_t w[D];
+    if (i < N) draw_words(i, w);
+    if (!MULTI) resolve_fat();
+    const bool reset = t == 1 || c.plan[t - 1].resampled != 0;
+    if (MULTI) {
+        __shared__ u64 s_w[APS_MAX_RANKS][4];
+        const u64 v0 = 0;
+        if (blockIdx.x == 0) mail_post(c.peers, c.rank, c.world, 2, seq0 + (u64)(t - 1) + 1, &v0, 1);
+        if (!(c.dbg & 1) && !mail_wait(c.peers, c.rank, c.world, 2, seq0 + (u64)(t - 1) + 1, s_w, 1, c.st->spin, &c.st->err, t == 1 ? 20 : 1))
+            c.st->err = APS_ERR_COMM;
+        __syncthreads();
+        resolve_fat();
+    }
+    for (bool first = true; i < N; i += stride, first = false) {
+        long long a = 0;
+        if (t > 1) a = MULTI ? __ldcg(anc + i) : anc[i];
+        double lw_old = 0.0;
+        if (!reset) lw_old = c.logw[i];
+        if (!first) draw_words(i, w);
+        double z[D];
+#pragma unroll
+        for (int j = 0; j < D / 2; ++j) aps_normal_pair(w[2 * j], w[2 * j + 1], &z[2 * j], &z[2 * j + 1]);
+        double x[D];
+        if (has_ref && c.slot0 + i == c.Ng - 1) {  // the reference keeps the globally last slot
+#pragma unroll
+            for (int k = 0; k < D; ++k) x[k] = c.ref[(t - 1) * D + k];
+        } else if (t == 1) {
+            aps_prior_draw<D>(&c.md, z, x);
+        } else {
+            const double *xsrc = xp;
+            if (multi && !(c.dbg & 4)) {
+                const unsigned al = (unsigned)(a - c.slot0);
+                if (al < (unsigned)N) {
+                    a = al;
+                } else {
+                    const int owner = (int)((unsigned)a / (unsigned)N);
+                    a -= (long long)owner * N;
+                    xsrc = c.peers->x[owner] + xoff;
+                }
+            }
+            double xg[D];
+#pragma unroll
+            for (int k = 0; k < D; ++k) xg[k] = xsrc[(long long)k * NS + a];
+            aps_trans_draw<D>(&c.md, xg, z, x);
+        }
+        const double ll = aps_obs_logpdf<D, DY, OBS>(&c.md, x, y);
+        const double lw = (reset ? 0.0 : lw_old) + ll;
+        if (lw != lw) bad = 1;
+        else {
+            mx = lw > mx ? lw : mx;
+            any = true;
+        }
+#pragma unroll
+        for (int k = 0; k < D; ++k) xt[(long long)k * NS + i] = x[k];
+        c.logw[i] = lw;
+    }
+    if (any) bmax = aps_encode_ordered(mx);
+    bmax = block_max_u64<APS_K1_THREADS / 32>(bmax, red);
+    bad = __syncthreads_or(bad);
+    if (threadIdx.x == 0) {
+        if (bmax) atomicMax(&c.acc[t].max_enc, bmax);
+        if (bad) atomicOr(&c.acc[t].bad, 1u);
+    }
+    if (multi) {
+        __shared__ unsigned s_lastb;
+        __shared__ u64 s_pub[2];
+        if (threadIdx.x == 0) {
+            __threadfence();
+            s_lastb = atomicAdd(&c.acc[t].k1_done, 1u) == gridDim.x - 1 ? 1u : 0u;
+            if (s_lastb) {
+                __threadfence();
+                s_pub[0] = atomicMax(&c.acc[t].max_enc, 0ull);
+                s_pub[1] = (u64)atomicOr(&c.acc[t].bad, 0u);
+            }
+        }
+        __syncthreads();
+        if (s_lastb) mail_post(c.peers, c.rank, c.world, 0, seq0 + (u64)t + 1, s_pub, 2);
+    }
+}
+
 // max of a plain vector (operator-level entry points)
 template <int INPUT>
 __global__ void __launch_bounds__(APS_K1_THREADS) k_vector_max(const double *__restrict__ in, long long n, StepAcc *acc) {
