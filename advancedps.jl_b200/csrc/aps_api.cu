@@ -461,7 +461,7 @@ extern "C" int aps_create(const aps_config *cfg, aps_handle **out) {
     // ---- fused persistent sweep: one CTA per SM, every CTA owns a contiguous chunk of slots
     // PDL: only where a step is exactly K1 -> K2 -> K3 (every kernel of the chain carries the wait)
     h->pdl = world == 1 && (cfg->resampler == APS_RESAMPLE_SYSTEMATIC || cfg->resampler == APS_RESAMPLE_STRATIFIED) &&
-             cfg->sampler != APS_PGAS && getenv("APS_PDL") != nullptr && atoi(getenv("APS_PDL")) != 0;
+             cfg->sampler != APS_PGAS && APS_PDL && getenv("APS_PDL") != nullptr && atoi(getenv("APS_PDL")) != 0;
     h->f_fused = nullptr;
     h->fused_forced = getenv("APS_FUSED") != nullptr && atoi(getenv("APS_FUSED")) != 0;
     if (world == 1 && getenv("APS_NO_FUSED") == nullptr) {

@@ -56,8 +56,25 @@ typedef unsigned long long u64;
 // predecessor is then complete and flushed). APS_PDL_TRIGGER() at the top of a kernel lets ITS
 // successor launch as soon as every block of this kernel is resident. Both are no-ops in a kernel
 // launched without the attribute.
+// Measured (round 2, C2): trigger at kernel start 3.08 ms per sweep, trigger after the main loop 2.68 ms,
+// no PDL 2.69 ms -- no gain, and the extra state costs the resample kernel its spill-free register
+// allocation (isolated N = 2^25: 85.8 -> 89.3 us). Hence a build option (-DAPS_PDL=1 and APS_PDL=1 in
+// the environment), off by default: the instructions are not even emitted.
+#ifndef APS_PDL
+#define APS_PDL 0
+#endif
+#if APS_PDL
 #define APS_PDL_WAIT() asm volatile("griddepcontrol.wait;" ::: "memory")
 #define APS_PDL_TRIGGER() asm volatile("griddepcontrol.launch_dependents;" ::: "memory")
+#else
+#define APS_PDL_WAIT() ((void)0)
+#define APS_PDL_TRIGGER() ((void)0)
+#endif
+// In-graph timeline probes of K2 / K3 (APS_DEBUG_MULTI & 16 prints first-block-start -> last-block-end per
+// kernel): -DAPS_TIMELINE=1 only, for the same reason. (K1 always carries its probe.)
+#ifndef APS_TIMELINE
+#define APS_TIMELINE 0
+#endif
 
 // ---------------------------------------------------------------- multi-GPU sharding (one process per GPU)
 // Rank r owns the contiguous global slots [r Nl, (r+1) Nl). Peers' state / ancestor stores and a

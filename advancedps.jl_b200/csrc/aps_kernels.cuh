@@ -512,7 +512,7 @@ __global__ void __launch_bounds__(APS_K2_THREADS) k_normalise(const __grid_const
     const long long base = (long long)blockIdx.x * APS_TILE;
     StepAcc *acc = &c.acc[s];
     APS_PDL_WAIT();
-    SpanProbe probe(acc, 1, c.dbg & 16);
+    SpanProbe probe(acc, 1, APS_TIMELINE && (c.dbg & 16));
     if (threadIdx.x < 3) s_tot[threadIdx.x] = 0;
     __syncthreads();
     u64 max_enc = acc->max_enc;
@@ -1015,7 +1015,7 @@ __global__ void __launch_bounds__(APS_K3_THREADS, MULTI ? APS_K3_MINBLOCKS - 2 :
     const int tid = threadIdx.x;
     if (DEFER && !MULTI) zero_own<APS_K3_THREADS, APS_K3_CPT>(own);   // (shared memory only: before the wait)
     APS_PDL_WAIT();
-    SpanProbe probe(&c.acc[s], 2, c.dbg & 16);
+    SpanProbe probe(&c.acc[s], 2, APS_TIMELINE && (c.dbg & 16));
     const long long base = (long long)blockIdx.x * APS_TILE;
     AncDst dst;
     dst.base = anc_out;
