@@ -43,7 +43,7 @@ typedef unsigned long long u64;
 #define APS_K3_MINBLOCKS 8
 #endif
 // 128 threads x 8 blocks per SM (64 registers): measured best at N = 1e6 (2.64 ms per sweep; 256 x 4: 2.74,
-// 128 x 10 at 48 registers: 2.72, 256 x 5 at 48 registers: 2.84 -- scratch/time_k1.py, round 2)
+// 128 x 10 at 48 registers: 2.72, 256 x 5 at 48 registers: 2.84 -- scripts/time_sweep_kernels.py, round 2)
 #ifndef APS_K1_THREADS
 #define APS_K1_THREADS 128      // threads per block of the grid-stride kernels (propagate, maxima)
 #endif
