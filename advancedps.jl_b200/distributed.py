@@ -24,6 +24,26 @@ def combine_totals(totals, rank):
     return sum(totals), sum(totals[:rank])
 
 
+def draw_partition(n_draws, world, rank):
+    """Philox blocks [p0, p1) whose i.i.d. draws (two per block) ``rank`` makes in the sharded
+    multinomial / residual step -- each draw is made once and routed to the rank that owns its weight
+    range (csrc: k_multi_route)."""
+    npairs = (int(n_draws) + 1) // 2
+    pp = (npairs + world - 1) // world
+    return min(rank * pp, npairs), min((rank + 1) * pp, npairs)
+
+
+def owner_of(tau, totals):
+    """Rank whose weight range [sum(totals[:r]), sum(totals[:r+1])) holds the integer position ``tau``,
+    and the position relative to that range."""
+    off = 0
+    for r, t in enumerate(totals):
+        if tau < off + int(t):
+            return r, tau - off
+        off += int(t)
+    raise ValueError("tau beyond the weight total")
+
+
 def create_sharded_handle(model, n_global, n_steps, Y, resampler=_abi.RESAMPLE_SYSTEMATIC,
                           ess_threshold=float("nan"), keep_history=True, device=None, group=None,
                           sampler=_abi.SAMPLER_SMC):

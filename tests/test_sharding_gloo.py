@@ -98,10 +98,11 @@ def test_shard_bounds_and_totals():
 
 
 def _worker_multinomial(rank, world, port, n_global, tmpdir):
-    """Sharded multinomial step as the kernels do it: every rank makes ALL draws (two per Philox
-    block), keeps those whose integer threshold falls into its own weight range, histograms them
-    over its own parents; offspring totals are exchanged so that children are laid out grouped by
-    parent in global parent order. Must equal the unsharded oracle's draw list."""
+    """Sharded multinomial step as the kernels do it (round 2): every draw is made ONCE -- rank r makes
+    the draws of its share of the Philox blocks (two draws per block) -- and ROUTED to the rank whose
+    weight range holds it; the owner histograms what it received over its own parents; offspring
+    totals are exchanged so that children are laid out grouped by parent in global parent order.
+    Must equal the unsharded oracle's draw list."""
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import ctypes as Ct
@@ -123,17 +124,21 @@ def _worker_multinomial(rank, world, port, n_global, tmpdir):
         dist.all_gather_object(tot, int(Qr))
         Q, offset = D.combine_totals(tot, rank)
         cum = np.cumsum(q.astype(object))                      # exact python ints, local inclusive sums
-        key, step, n = 99, 4, n_global
-        counts = np.zeros(hi - lo, dtype=np.int64)
-        for p in range((n + 1) // 2):                          # every rank makes all draws
+        key, step, n = 99, 4, n_global - 1                     # n = N - 1 draws: the PG case (odd count, last block half used)
+        p0, p1 = D.draw_partition(n, world, rank)
+        send = [[] for _ in range(world)]                      # positions relative to the owner's range
+        for p in range(p0, p1):                                # this rank's share of the draws
             w = O.philox2x64(p, (step << 16) | (1 << 8), key)
             for h in range(2):
-                i = 2 * p + h
-                if i >= n:
-                    continue
-                tau = ((w[h] >> 11) * Q) >> 53
-                if offset <= tau < offset + int(Qr):           # ... and keeps those in its own range
-                    counts[int(np.searchsorted(cum, tau - offset, side="right"))] += 1
+                if 2 * p + h < n:
+                    o, rel = D.owner_of(((w[h] >> 11) * Q) >> 53, tot)
+                    send[o].append(rel)
+        routed = [None] * world                                # the all-to-all of k_multi_route
+        dist.all_gather_object(routed, send)
+        counts = np.zeros(hi - lo, dtype=np.int64)
+        for src in range(world):
+            for rel in routed[src][rank]:
+                counts[int(np.searchsorted(cum, rel, side="right"))] += 1
         ctot = [None] * world
         dist.all_gather_object(ctot, int(counts.sum()))
         assert sum(ctot) == n
@@ -147,9 +152,9 @@ def _worker_multinomial(rank, world, port, n_global, tmpdir):
         # unsharded oracle: draw list -> counts -> grouped by parent (src/container.jl:185-217)
         qa, _, Qa = O.quantise_logw(logw_all)
         idx = np.zeros(n, dtype=np.int64)
-        O._chk(O.lib().orc_resample_multinomial_canon(O._ptr(qa), Ct.c_int64(n), Ct.c_int64(n), Ct.c_uint64(key),
+        O._chk(O.lib().orc_resample_multinomial_canon(O._ptr(qa), Ct.c_int64(n_global), Ct.c_int64(n), Ct.c_uint64(key),
                                                       Ct.c_uint64(step), O._ptr(idx)))
-        want = np.repeat(np.arange(n), np.bincount(idx - 1, minlength=n))
+        want = np.repeat(np.arange(n_global), np.bincount(idx - 1, minlength=n_global))
         np.save(os.path.join(tmpdir, f"okm_{rank}.npy"), np.array([int(Qa == Q and np.array_equal(anc, want))]))
     finally:
         dist.destroy_process_group()
@@ -159,3 +164,18 @@ def test_two_rank_sharded_multinomial_matches_unsharded(tmp_path):
     port = 29900 + (os.getpid() % 90)
     mp.spawn(_worker_multinomial, args=(2, port, 2048, str(tmp_path)), nprocs=2, join=True)
     assert all(int(np.load(tmp_path / f"okm_{r}.npy")[0]) == 1 for r in range(2))
+
+
+def test_draw_partition_and_owner():
+    sys.path.insert(0, ROOT)
+    from advancedps_b200 import distributed as D
+
+    for n, world in ((10, 2), (11, 4), (1, 8), (8_000_000, 8), (7_999_999, 8)):
+        parts = [D.draw_partition(n, world, r) for r in range(world)]
+        assert parts[0][0] == 0 and parts[-1][1] == (n + 1) // 2
+        assert all(parts[r][1] == parts[r + 1][0] for r in range(world - 1))   # contiguous, no draw twice
+    assert D.owner_of(0, [5, 0, 7]) == (0, 0)
+    assert D.owner_of(5, [5, 0, 7]) == (2, 0)      # an empty range owns nothing
+    assert D.owner_of(11, [5, 0, 7]) == (2, 6)
+    with pytest.raises(ValueError):
+        D.owner_of(12, [5, 0, 7])
