@@ -204,6 +204,17 @@ __device__ __forceinline__ ulonglong2 ld_pair_sys(const ulonglong2 *p) {
                  : "memory");
     return r;
 }
+// Last-block detection (device scope). A block publishes its results (plain stores / relaxed atomics), then takes a
+// ticket with RELEASE semantics; the block that draws the last ticket fences (acquire) and reads what the others
+// published. `__threadfence(); atomicAdd()` does the same but compiles to MEMBAR.SC.GPU + CCTL.IVALL -- a sequentially
+// consistent fence plus an invalidate of the SM's whole L1, paid by EVERY block and felt by its neighbours on the SM --
+// where the release atomic is MEMBAR.ALL.GPU + ATOMG and only the last block invalidates (cuobjdump, round 2).
+__device__ __forceinline__ unsigned ticket_release(unsigned *ctr, unsigned v) {
+    unsigned r;
+    asm volatile("atom.add.release.gpu.global.u32 %0, [%1], %2;" : "=r"(r) : "l"(ctr), "r"(v) : "memory");
+    return r;
+}
+__device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
 __device__ __forceinline__ void fence_acq_rel_sys() { asm volatile("fence.acq_rel.sys;" ::: "memory"); }
 // publish nv values of this rank (threads 0..world-1 of ONE block; thread r writes to rank r)
 __device__ __forceinline__ void mail_post(const PeerTable *pt, int rank, int world, int kind, u64 seq, const u64 *v,
@@ -268,6 +279,8 @@ struct StepAcc {
     u64 tot[4];                 // sharded: this rank's integer totals (Q, Q1, Q2 | nan-flag) and the global max
     u64 rank_off;               // sharded: weight total of the lower ranks at this decision point
     long long child_off;        // sharded multinomial / residual: children owned by parents of lower ranks
+    int safe_lo, safe_hi;       // sharded: global child slots [safe_lo, safe_hi) descend from THIS rank's parents (block 0 of
+                                // k_resample; empty when unknown) -- the next propagate kernel handles them before the scatter barrier
     u64 t_first_neg[3];         // diagnostics (APS_DEBUG_SPAN): ~globaltimer of the first block start per kernel
     u64 t_last[3];              // globaltimer of the last block end per kernel
 };

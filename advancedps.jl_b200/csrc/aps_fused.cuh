@@ -149,8 +149,8 @@ __device__ __forceinline__ ulonglong2 wait_pair(const ulonglong2 *p, u64 seq, in
 
 // arrival: (block barrier first, by the caller) entry stores by this thread, fence, one L2 atomic
 __device__ __forceinline__ void ex_arrive(u64 *ctr) {
-    __threadfence();
-    atomicAdd(ctr, 1ull);
+    // release: MEMBAR.ALL.GPU + RED (no sequentially consistent fence, no L1 invalidate on the producer side)
+    asm volatile("red.release.gpu.global.add.u64 [%0], %1;" ::"l"(ctr), "l"(1ull) : "memory");
 }
 // one thread polls the counter until `target` CTAs have arrived; ~3 s budget (a CTA that never
 // arrives means the launch was not co-resident -- a bug, not a runtime condition: fail loudly)
@@ -166,7 +166,7 @@ __device__ __forceinline__ void ex_wait(const u64 *ctr, u64 target, int *err) {
             }
         }
     }
-    __threadfence();
+    fence_acq_rel_gpu();   // acquire (with the block barrier that follows in the caller)
 }
 
 // ---------------------------------------------------------------- the sweep

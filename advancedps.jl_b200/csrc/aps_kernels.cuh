@@ -151,31 +151,51 @@ __global__ void APS_K1_BOUNDS k_propagate(const __grid_constant__ DevCtx c, cons
     // log-weights start at zero in every sweep (src/smc.jl:45-51); afterwards they restart from
     // zero only when the previous decision point resampled (reset_logweights!, container.jl:228)
     const bool reset = t == 1 || c.plan[t - 1].resampled != 0;
+    // Sharded: the ancestor scatter of step t-1 (peer stores from every rank) must have landed before the
+    // slots it touches are read: this rank's resample kernel is complete (stream order), so block 0 tells
+    // every rank, and every block waits until all ranks said so. At t = 1 the same exchange makes sure
+    // every rank has finished its previous sweep (and trajectory extraction) before any state slab is
+    // overwritten.
+    // Most slots do not depend on a peer at all: the children of this rank's OWN parents -- global slots
+    // [safe_lo, safe_hi), recorded by block 0 of the resample kernel -- have their ancestor entries written
+    // by this rank's resample kernel (complete: stream order) and their parents' states in the local slab.
+    // Iterations whose 256 slots lie inside that range run BEFORE the wait (phase 0), so the NVLink
+    // traversal of the barrier and the skew between the ranks hide behind them; the others follow the
+    // wait (phase 1). Not at t = 1, and not when this rank deferred children of fat parents (their
+    // ranges cross the safe slots; the list is read after the barrier only).
+    __shared__ u64 s_w[APS_MAX_RANKS][4];
+    bool early = false;
+    int safe_lo = 0, safe_hi = 0;
     if (MULTI) {
-        // the ancestor scatter of step t-1 (peer stores from every rank) must have landed: this
-        // rank's resample kernel is complete (stream order), so block 0 tells every rank, and
-        // every block waits until all ranks said so. At t = 1 the same exchange makes sure every
-        // rank has finished its previous sweep (and trajectory extraction) before any state
-        // slab is overwritten.
-        __shared__ u64 s_w[APS_MAX_RANKS][4];
         const u64 v0 = 0;
         if (blockIdx.x == 0) mail_post(c.peers, c.rank, c.world, 2, seq0 + (u64)(t - 1) + 1, &v0, 1);
-        if (!(c.dbg & 1) && !mail_wait(c.peers, c.rank, c.world, 2, seq0 + (u64)(t - 1) + 1, s_w, 1, c.st->spin, &c.st->err, t == 1 ? 20 : 1))
-            c.st->err = APS_ERR_COMM;
-        __syncthreads();
-        resolve_fat();  // the peers' pushes into this rank's list are complete now
+        if (t > 1 && !(c.dbg & 2)) {
+            safe_lo = c.acc[t - 1].safe_lo;
+            safe_hi = c.acc[t - 1].safe_hi;
+            early = safe_hi > safe_lo && __ldcg(&c.fat_cnt[t - 1]) == 0;
+        }
     }
+    const long long stride = (long long)gridDim.x * APS_K1_THREADS;
+    // block-uniform: do all slots of the block's iteration that starts at pair pb descend from this rank's parents?
+    auto iteration_is_safe = [&](long long pb) {
+        const long long g0 = c.slot0 + 2 * pb, g1 = g0 + 2 * APS_K1_THREADS;
+        return early && g0 >= safe_lo && (g1 < c.slot0 + N ? g1 : c.slot0 + N) <= safe_hi;
+    };
+    bool need_wait = !early;   // a block whose iterations are all safe does not depend on the peers at all
+    if (MULTI && early)
+        for (long long pb = (long long)blockIdx.x * APS_K1_THREADS; pb < npairs; pb += stride) need_wait = need_wait || !iteration_is_safe(pb);
+    long long wp = p;   // the pair whose random words are in w
     // Order inside one iteration: ancestor indices first (they are needed for the only dependent load
     // chain of the loop), then the integer-only Philox rounds while they arrive, then the parent-state
     // gather, then the floating-point half of the draw (log / sqrt / sincospi) while THAT is in flight.
-    for (bool first = true; p < npairs; p += (long long)gridDim.x * APS_K1_THREADS, first = false) {
+    auto body = [&](const long long p) {
         const long long i0 = 2 * p;
         int2 a2 = make_int2(0, 0);
         if (t > 1) a2 = MULTI ? __ldcg(reinterpret_cast<const int2 *>(anc + i0))   // scattered by the peers: read at L2
                               : *reinterpret_cast<const int2 *>(anc + i0);
         double2 lw2 = make_double2(0.0, 0.0);
         if (!reset) lw2 = *reinterpret_cast<const double2 *>(c.logw + i0);
-        if (!first) aps_pair_words<D>(key, (u64)(pair0 + p), (u64)t, w);
+        if (p != wp) aps_pair_words<D>(key, (u64)(pair0 + p), (u64)t, w);
         double z[2 * D];
         if (D > 2) aps_words_to_normals<D>(w, z);   // (d >= 3: registers are the limit -- finish the draw before the gather)
         double xg[2][D];   // parent states of the two slots
@@ -236,6 +256,24 @@ __global__ void APS_K1_BOUNDS k_propagate(const __grid_constant__ DevCtx c, cons
         for (int k = 0; k < D; ++k)
             *reinterpret_cast<double2 *>(xt + (long long)k * NS + i0) = make_double2(xo[0][k], xo[1][k]);
         *reinterpret_cast<double2 *>(c.logw + i0) = make_double2(lwo[0], lwo[1]);
+    };
+    if (!MULTI) {
+        for (; p < npairs; p += stride) body(p);
+    } else {
+#pragma unroll 1
+        for (int phase = early ? 0 : 1; phase < (need_wait ? 2 : 1); ++phase) {
+            if (phase == 1) {
+                if (!(c.dbg & 1) && !mail_wait(c.peers, c.rank, c.world, 2, seq0 + (u64)(t - 1) + 1, s_w, 1, c.st->spin, &c.st->err, t == 1 ? 20 : 1))
+                    c.st->err = APS_ERR_COMM;
+                __syncthreads();
+                resolve_fat();  // the peers' pushes into this rank's list are complete now
+            }
+#pragma unroll 1
+            for (long long pb = (long long)blockIdx.x * APS_K1_THREADS; pb < npairs; pb += stride) {
+                if (iteration_is_safe(pb) != (phase == 0)) continue;
+                if (pb + threadIdx.x < npairs) body(pb + threadIdx.x);
+            }
+        }
     }
     if (any) bmax = aps_encode_ordered(mx);
     if (!(c.dbg & 512)) APS_PDL_TRIGGER();   // this block's stores are issued: the next kernel may start launching
@@ -245,16 +283,15 @@ __global__ void APS_K1_BOUNDS k_propagate(const __grid_constant__ DevCtx c, cons
         if (bmax) atomicMax(&c.acc[t].max_enc, bmax);
         if (bad) atomicOr(&c.acc[t].bad, 1u);
     }
-    if (multi) {
+    if (multi && !(c.dbg & 64)) {   // (64: timing diagnostics only, with 1)
         // all-reduce(max), producer side: the last block to finish publishes this shard's maximum
         // to every rank, so it is on its way while this kernel drains and k_normalise launches
         __shared__ unsigned s_lastb;
         __shared__ u64 s_pub[2];
         if (threadIdx.x == 0) {
-            __threadfence();
-            s_lastb = atomicAdd(&c.acc[t].k1_done, 1u) == gridDim.x - 1 ? 1u : 0u;
+            s_lastb = ticket_release(&c.acc[t].k1_done, 1u) == gridDim.x - 1 ? 1u : 0u;
             if (s_lastb) {
-                __threadfence();
+                fence_acq_rel_gpu();
                 s_pub[0] = atomicMax(&c.acc[t].max_enc, 0ull);
                 s_pub[1] = (u64)atomicOr(&c.acc[t].bad, 0u);
             }
@@ -380,10 +417,9 @@ __global__ void __launch_bounds__(APS_K1_THREADS, APS_K1P_MINBLOCKS) k_propagate
         __shared__ unsigned s_lastb;
         __shared__ u64 s_pub[2];
         if (threadIdx.x == 0) {
-            __threadfence();
-            s_lastb = atomicAdd(&c.acc[t].k1_done, 1u) == gridDim.x - 1 ? 1u : 0u;
+            s_lastb = ticket_release(&c.acc[t].k1_done, 1u) == gridDim.x - 1 ? 1u : 0u;
             if (s_lastb) {
-                __threadfence();
+                fence_acq_rel_gpu();
                 s_pub[0] = atomicMax(&c.acc[t].max_enc, 0ull);
                 s_pub[1] = (u64)atomicOr(&c.acc[t].bad, 0u);
             }
@@ -596,13 +632,12 @@ __global__ void __launch_bounds__(APS_K2_THREADS) k_normalise(const __grid_const
         return;
     }
     if (threadIdx.x == 0) {
-        __threadfence();
-        const unsigned ticket = atomicAdd(&acc->done_ctr, 1u);
+        const unsigned ticket = ticket_release(&acc->done_ctr, 1u);
         s_last = (ticket == gridDim.x - 1) ? 1u : 0u;
     }
     __syncthreads();
     if (!s_last) return;
-    __threadfence();
+    fence_acq_rel_gpu();
 
     // ---- last block: exclusive scan of the tile totals (each thread owns a contiguous chunk)
     const long long nt = c.num_tiles;
@@ -1064,7 +1099,7 @@ __global__ void __launch_bounds__(APS_K3_THREADS, MULTI ? APS_K3_MINBLOCKS - 2 :
 #endif
     }
     const u64 step = (u64)(s + c.ctr_offset);
-    u64 tprefix = 0;
+    u64 tprefix = 0, shard_q = 0;   // (shard_q: total weight of this rank's tiles, deferred plan only)
     if (!defer) tprefix = c.tile_prefix[blockIdx.x];
 
     if (!(DEFER && !MULTI)) zero_own<APS_K3_THREADS, APS_K3_CPT>(own);
@@ -1097,6 +1132,7 @@ __global__ void __launch_bounds__(APS_K3_THREADS, MULTI ? APS_K3_MINBLOCKS - 2 :
         }
         __syncthreads();
         tprefix = s_acc4[3];
+        shard_q = s_acc4[0];
         if (tid == 0) c.tile_prefix[blockIdx.x] = s_acc4[3];  // (local) prefix, kept for the final pick (k_pick)
         if (MULTI) {
             // sharded: these are the SHARD totals. Block 0 publishes them to every rank (all-gather,
@@ -1204,10 +1240,21 @@ __global__ void __launch_bounds__(APS_K3_THREADS, MULTI ? APS_K3_MINBLOCKS - 2 :
         pp = &s_plan;
         tprefix += s_off;
         if (!pp->resampled || pp->err) {
+            if (blockIdx.x == 0 && tid == 0 && !pp->err) {   // identity ancestors: every slot of this rank is its own parent
+                c.acc[s].safe_lo = (int)c.slot0;
+                c.acc[s].safe_hi = (int)(c.slot0 + N);
+            }
             identity_ancestors();
             return;
         }
         load_plan();
+        if (blockIdx.x == 0 && tid == 64) {
+            // the child slots that descend from this rank's parents, [K(offset), K(offset + shard total)): exact
+            // (128-bit fix-up where the estimate is within its guard band). k_propagate runs them before the barrier.
+            const u64 shard_total = defer ? shard_q : c.acc[s].tot[0];
+            c.acc[s].safe_lo = (c.slot0 == 0) ? 0 : children_below_checked<KIND>(s_off, Q, R, n, ratio, roff, guard, key, step);
+            c.acc[s].safe_hi = children_below_checked<KIND>(s_off + shard_total, Q, R, n, ratio, roff, guard, key, step);
+        }
     }
     excl += tprefix;
 
@@ -1626,10 +1673,9 @@ __global__ void __launch_bounds__(APS_THREADS) k_residual_split(const __grid_con
     if (threadIdx.x == 0) {
         a.tile_count[blockIdx.x] = (int)sd;
         atomicAdd(&rs->sum_d, sd);
-        __threadfence();
-        const unsigned ticket = atomicAdd(&rs->done_ctr, 1u);
+        const unsigned ticket = ticket_release(&rs->done_ctr, 1u);
         if (ticket == gridDim.x - 1 && !a.child_off) {  // sharded: k_residual_exchange<0> combines the ranks
-            __threadfence();
+            fence_acq_rel_gpu();
             const u64 tot = atomicAdd(&rs->sum_d, 0ull);
             const long long rc = (long long)n - (long long)tot;
             rs->n_rest = rc;
@@ -1662,13 +1708,12 @@ __global__ void __launch_bounds__(APS_THREADS) k_residual_weights(const __grid_c
     s0 = block_sum_u64<APS_WARPS>(s0, red);
     if (threadIdx.x == 0) {
         tile_sum[blockIdx.x] = s0;
-        __threadfence();
-        const unsigned ticket = atomicAdd(done_ctr, 1u);
+        const unsigned ticket = ticket_release(done_ctr, 1u);
         s_last = (ticket == gridDim.x - 1) ? 1u : 0u;
     }
     __syncthreads();
     if (!s_last) return;
-    __threadfence();
+    fence_acq_rel_gpu();
     const long long nt = a.num_tiles;
     const long long per = (nt + APS_THREADS - 1) / APS_THREADS;
     const long long lo = (long long)threadIdx.x * per;
@@ -1866,13 +1911,12 @@ __global__ void __launch_bounds__(APS_THREADS) k_pgas_select(const __grid_consta
     // tile_s1 is free at this point of the step (the plan of s is already written)
     if (threadIdx.x == 0) {
         c.tile_s1[blockIdx.x] = s0;
-        __threadfence();
-        const unsigned ticket = atomicAdd(&acc->sel_done_ctr, 1u);
+        const unsigned ticket = ticket_release(&acc->sel_done_ctr, 1u);
         s_last = (ticket == gridDim.x - 1) ? 1u : 0u;
     }
     __syncthreads();
     if (!s_last) return;
-    __threadfence();
+    fence_acq_rel_gpu();
     const long long nt = c.num_tiles;
     const long long per = (nt + APS_THREADS - 1) / APS_THREADS;
     const long long lo = (long long)threadIdx.x * per;
@@ -2076,12 +2120,11 @@ __global__ void __launch_bounds__(APS_K1_THREADS) k_smooth_step(const __grid_con
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-        __threadfence();
-        s_last = atomicAdd(done_ctr + (t - 1), 1u) == gridDim.x - 1 ? 1u : 0u;
+        s_last = ticket_release(done_ctr + (t - 1), 1u) == gridDim.x - 1 ? 1u : 0u;
     }
     __syncthreads();
     if (!s_last) return;
-    __threadfence();
+    fence_acq_rel_gpu();
     if (threadIdx.x < D) {
         double v = 0.0;
         for (unsigned b = 0; b < gridDim.x; ++b) v += __ldcg(&partial[(long long)b * APS_MAX_D + threadIdx.x]);
