@@ -97,13 +97,23 @@ class _PinnedPool:
         if lst:
             p = lst.pop()
         else:
-            p = C.c_void_p()
-            check(lib().aps_host_alloc(C.c_int64(nbytes), C.byref(p)))
-            p = p.value
+            p = self._alloc(nbytes)
+            if nbytes not in self.free:
+                # first buffer of this size: page-lock a spare one as well. A caller that keeps the previous
+                # result alive while the next call runs (`w = sample(...).weights` in a loop) alternates between
+                # two buffers; without the spare, the second one would be page-locked (milliseconds, and it
+                # stalls the device) inside the caller's steady-state loop.
+                self.free[nbytes] = [self._alloc(nbytes)]
         buf = (C.c_char * nbytes).from_address(p)
         a = np.frombuffer(buf, dtype=dtype, count=int(n))
         weakref.finalize(buf, self._give_back, nbytes, p)   # `a` keeps `buf` alive through its base
         return a
+
+    @staticmethod
+    def _alloc(nbytes):
+        p = C.c_void_p()
+        check(lib().aps_host_alloc(C.c_int64(nbytes), C.byref(p)))
+        return p.value
 
     def _give_back(self, nbytes, p):
         lst = self.free.setdefault(nbytes, [])
