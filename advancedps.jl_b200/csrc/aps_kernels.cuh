@@ -283,9 +283,11 @@ __global__ void APS_K1_BOUNDS k_propagate(const __grid_constant__ DevCtx c, cons
         if (bmax) atomicMax(&c.acc[t].max_enc, bmax);
         if (bad) atomicOr(&c.acc[t].bad, 1u);
     }
-    if (multi && !(c.dbg & 64)) {   // (64: timing diagnostics only, with 1)
+    if (multi && (c.dbg & 64)) {   // (64: the round-1 scheme, kept for A/B timing -- block 0 of k_normalise posts otherwise)
         // all-reduce(max), producer side: the last block to finish publishes this shard's maximum
-        // to every rank, so it is on its way while this kernel drains and k_normalise launches
+        // to every rank, so it is on its way while this kernel drains and k_normalise launches.
+        // Measured (2 x B200): the ticket and, above all, the remote store at the very end of the kernel --
+        // the grid is not complete before NVLink has acknowledged it -- cost 1.7 us per step
         __shared__ unsigned s_lastb;
         __shared__ u64 s_pub[2];
         if (threadIdx.x == 0) {
@@ -413,7 +415,7 @@ __global__ void __launch_bounds__(APS_K1_THREADS, APS_K1P_MINBLOCKS) k_propagate
         if (bmax) atomicMax(&c.acc[t].max_enc, bmax);
         if (bad) atomicOr(&c.acc[t].bad, 1u);
     }
-    if (multi) {
+    if (multi && (c.dbg & 64)) {   // (see k_propagate)
         __shared__ unsigned s_lastb;
         __shared__ u64 s_pub[2];
         if (threadIdx.x == 0) {
@@ -567,9 +569,16 @@ __global__ void __launch_bounds__(APS_K2_THREADS) k_normalise(const __grid_const
         // all-reduce(max): every block combines the shard maxima published by the propagate kernels
         __shared__ u64 s_m[APS_MAX_RANKS][4];
         __shared__ int s_okm;
-        if (threadIdx.x == 0) s_okm = 1;
+        __shared__ u64 s_pubm[2];
+        if (threadIdx.x == 0) {
+            s_okm = 1;
+            s_pubm[0] = max_enc;       // this shard's maximum: the propagate kernel is complete (stream order)
+            s_pubm[1] = (u64)acc->bad;
+        }
         __syncthreads();
-        // (published by the last block of every rank's propagate kernel)
+        // producer side: block 0 publishes the shard maximum to every rank at the START of this kernel, so the
+        // NVLink traversal overlaps the kernel instead of holding the end of the propagate kernel
+        if (blockIdx.x == 0 && !(c.dbg & 64)) mail_post(c.peers, c.rank, c.world, 0, seq, s_pubm, 2);
         if (!(c.dbg & 1) && !mail_wait(c.peers, c.rank, c.world, 0, seq, s_m, 2, c.st ? c.st->spin : nullptr, c.st ? &c.st->err : nullptr)) s_okm = 0;
         if (c.dbg & 1) { if (threadIdx.x < c.world) { s_m[threadIdx.x][0] = acc->max_enc; s_m[threadIdx.x][1] = 0; } }
         __syncthreads();
