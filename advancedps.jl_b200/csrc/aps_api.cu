@@ -227,12 +227,21 @@ static int stride_grid(long long n) {
     return (int)(need < cap ? need : cap);
 }
 
+#ifndef APS_PREDRAW_MIN_TILES
+#define APS_PREDRAW_MIN_TILES 190
+#endif
 // ------------------------------------------------------------------ handle
 struct aps_handle {
     aps_config cfg;
     DevCtx ctx;
     cudaStream_t stream;
     cudaEvent_t ev0, ev1;
+    // pre-drawn normals (k_draw_normals) on a parallel, low-priority branch of the sweep's graph
+    cudaStream_t stream_draw[2];
+    cudaEvent_t ev_fork, ev_join[2];
+    void (*f_draw)(DevCtx, long long);
+    int grid_draw, threads_draw, draw_ahead;   // draw_ahead: 1 or 2 steps (2: two buffers, the draws of step t + 2 are forked behind propagate(t))
+    long long zbuf_stride;
     SweepParams *d_sp;
     double *d_ref, *d_traj, *d_Y, *d_scratch;  // d_scratch: N x d doubles for accessors
     // multinomial / residual resampling scratch
@@ -277,6 +286,12 @@ static void free_handle(aps_handle *h) {
     if (!h) return;
     cudaSetDevice(h->cfg.device);
     if (h->graph_ready) cudaGraphExecDestroy(h->graph);
+    cudaFree(h->ctx.zbuf);
+    for (int k = 0; k < 2; ++k) {
+        if (h->stream_draw[k]) cudaStreamDestroy(h->stream_draw[k]);
+        if (h->ev_join[k]) cudaEventDestroy(h->ev_join[k]);
+    }
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     cudaFree(h->ctx.x);
     cudaFree(h->ctx.anc);
     cudaFree(h->ctx.logw);
@@ -452,6 +467,39 @@ extern "C" int aps_create(const aps_config *cfg, aps_handle **out) {
     c.sp = h->d_sp;
     h->f_prop = pick_propagate(cfg->model.obs_kind, d, cfg->model.dy, world > 1);
     h->prop_per_slot = d == 4 && getenv("APS_K1_PAIRS") == nullptr;
+    // Pre-drawn normals (pair kernel, d <= 3): k_draw_normals(t + 1) runs beside k_normalise(t) / k_resample(t)
+    // Measured at the headline shape (N = 1e6 per GPU, profiles/README.md): one 128-thread block per SM, forked
+    // behind the propagate kernel, one step ahead; more threads per SM and the neighbouring kernel's span
+    // jumps to the draw kernel's duration. Enabled where the normalise / resample kernels are a single
+    // wave (<= 740 tiles, N <= 1.5e6 per GPU) -- beyond that the window beside them is shorter than the draw
+    // kernel at this size and the propagate kernel would wait for it -- and large enough that a step is not
+    // launch-bound (>= 190 tiles, N >= ~4e5: at 1e5 / 3e5 the extra graph node and its two edges cost 2-3 %; measured gain 3 % at 4e5, 8.5 % at 1e6, 5 % at 1.5e6).
+    // APS_PREDRAW=1 forces, APS_NO_PREDRAW=1 disables.
+    const bool predraw_ok = (c.num_tiles >= APS_PREDRAW_MIN_TILES && c.num_tiles <= 740) ||
+                            (getenv("APS_PREDRAW") != nullptr && atoi(getenv("APS_PREDRAW")) != 0);
+    if (!h->prop_per_slot && d <= 3 && predraw_ok && getenv("APS_NO_PREDRAW") == nullptr) {
+        h->f_draw = d == 1 ? k_draw_normals<1> : d == 2 ? k_draw_normals<2> : k_draw_normals<3>;
+        prefer_max_smem(h->f_draw);   // same carve-out as its neighbours: an SM that had to re-partition would serialise them
+        const long long npairs = (Nl + 1) / 2;
+        h->draw_ahead = 1;
+        if (const char *e = getenv("APS_DRAW_AHEAD")) h->draw_ahead = atoi(e) == 2 ? 2 : 1;
+        h->zbuf_stride = npairs * 2 * d;
+        CUH(cudaMalloc(&c.zbuf, sizeof(double) * (size_t)h->zbuf_stride * 2));
+        int lo_prio = 0, hi_prio = 0;
+        cudaDeviceGetStreamPriorityRange(&lo_prio, &hi_prio);   // (numerically: lo = least urgent)
+        for (int k = 0; k < 2; ++k) {
+            CUH(cudaStreamCreateWithPriority(&h->stream_draw[k], cudaStreamNonBlocking, lo_prio));
+            CUH(cudaEventCreateWithFlags(&h->ev_join[k], cudaEventDisableTiming));
+        }
+        CUH(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+        int bps = 1;   // blocks per SM of the draw kernel: a background trickle that fills idle issue slots, not SMs
+        if (const char *e = getenv("APS_DRAW_BPS")) bps = atoi(e) > 0 ? atoi(e) : bps;
+        h->threads_draw = 128;
+        if (const char *e = getenv("APS_DRAW_THREADS")) h->threads_draw = atoi(e) >= 32 && atoi(e) <= 512 ? (atoi(e) & ~31) : 128;
+        long long g = (npairs + h->threads_draw - 1) / h->threads_draw;
+        if (g > (long long)bps * sm_count()) g = (long long)bps * sm_count();
+        h->grid_draw = (int)(g < 1 ? 1 : g);
+    }
     prefer_max_smem(h->f_prop);
     h->f_res = pick_resample(cfg->resampler, world > 1, c.defer_plan != 0);
     h->f_pmax = pick_pgas_max(d);
@@ -724,10 +772,45 @@ static long long enqueue_sweep(aps_handle *h, LaunchProf *prof = nullptr) {
     k_init_sweep<<<1, 32, 0, st>>>(c);
     ++L.n;
     const int gt = (int)c.num_tiles;
+    // Pre-drawn normals (k_draw_normals). The draws of step u are forked behind propagate(u - A) -- which has
+    // consumed the buffer they go to -- onto a low-priority stream, run beside the kernels in between, and are
+    // joined before propagate(u); A = draw_ahead = 2 gives them more than a whole step (two buffers, two
+    // streams: consecutive draw kernels may overlap). Under stream capture these are parallel branches of the
+    // graph. With per-launch profiling everything stays on one stream (class 0, A = 1).
+    const bool draw = c.zbuf != nullptr;
+    const bool fork = draw && prof == nullptr && getenv("APS_DRAW_SERIAL") == nullptr;
+    const int A = fork ? h->draw_ahead : 1;
+    const bool fork_late = fork && getenv("APS_DRAW_FORK") != nullptr && atoi(getenv("APS_DRAW_FORK")) == 2;
+    auto ctx_for = [&](long long u) {   // the context of step u: its buffer of normals
+        DevCtx cc = c;
+        if (draw) cc.zbuf = c.zbuf + (A == 2 ? (u & 1) * h->zbuf_stride : 0);
+        return cc;
+    };
+    if (draw)
+        for (long long u = 1; u <= A && u <= c.T; ++u) {
+            h->f_draw<<<h->grid_draw, h->threads_draw, 0, st>>>(ctx_for(u), u);
+            ++L.n;
+        }
     for (long long t = 1; t <= c.T; ++t) {
-        launch_propagate(h, c, t, L);
+        launch_propagate(h, ctx_for(t), t, L);
+        const long long u = t + A;   // the draws that may now overwrite the buffer propagate(t) has read
+        auto fork_draws = [&]() {
+            if (fork) {
+                cudaStream_t sd = h->stream_draw[u & 1];
+                cudaEventRecord(h->ev_fork, st);
+                cudaStreamWaitEvent(sd, h->ev_fork, 0);
+                h->f_draw<<<h->grid_draw, h->threads_draw, 0, sd>>>(ctx_for(u), u);
+                cudaEventRecord(h->ev_join[u & 1], sd);
+                ++L.n;
+            } else {
+                APS_LAUNCH(0, h->f_draw<<<h->grid_draw, h->threads_draw, 0, st>>>(ctx_for(u), u));
+            }
+        };
+        if (draw && u <= c.T && !fork_late) fork_draws();
         APS_LAUNCH(1, launch_pdl(k_normalise<IN_LOGW>, gt, APS_K2_THREADS, 0, st, h->pdl, c, (const double *)c.logw, (long long)t));
+        if (draw && u <= c.T && fork_late) fork_draws();   // beside the resample kernel only (its issue slots are 70 % idle)
         launch_decision(h, c, t, h->f_res, L);
+        if (fork && t + 1 <= c.T && t + 1 > A) cudaStreamWaitEvent(st, h->ev_join[(t + 1) & 1], 0);   // the draws of step t + 1
     }
     launch_fill_fat(h, c, c.T, L);
     return L.n;
@@ -880,6 +963,7 @@ extern "C" int aps_sweep_profiled(aps_handle *h, uint64_t master_seed, const dou
 static DevCtx pc_ctx(aps_handle *h) {
     DevCtx c = h->ctx;
     c.defer_plan = 0;
+    c.zbuf = nullptr;   // (the stepwise container draws inside the propagate kernel)
     return c;
 }
 #define NEED_PC(name)                                                                               \

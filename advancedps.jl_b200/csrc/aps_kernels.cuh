@@ -62,6 +62,9 @@ struct DevCtx {
     u64 *rank_woff;                // [fat_steps][APS_MAX_RANKS + 1] exclusive weight prefix of the ranks for the draws of a step
     long long n_override;  // operator level: number of indices to draw (0: N, or N-1 with a reference)
     long long ctr_offset;  // operator level: Philox step counter = plan index + ctr_offset
+    // pre-drawn standard normals of the NEXT propagate kernel (k_draw_normals; null: the propagate kernel draws itself):
+    // [local pair][2 d] doubles, the pair layout of aps_pair_normals
+    double *zbuf;
 };
 
 enum { IN_LOGW = 0, IN_W = 1, IN_Q = 2 };
@@ -89,6 +92,40 @@ __global__ void k_init_sweep(const __grid_constant__ DevCtx c) {
         c.st->err = 0;
         c.st->picked_slot = -1;
         c.st->spin[0] = c.st->spin[1] = c.st->spin[2] = c.st->spin[3] = 0;
+    }
+}
+
+// ---------------------------------------------------------------- K0: the state draws of step t, ahead of time
+// The standard normals of a step depend on nothing but (key, slot, t) -- half of the propagate kernel's
+// instructions (10 Philox rounds, log, sqrt, sincospi per pair) wait for no data. This kernel makes them for
+// step t + 1 on a parallel branch of the sweep's graph while the normalise and resample kernels of step t --
+// one wave or less each, latency-bound, issue slots mostly idle -- occupy the stream; the propagate kernel then
+// only loads them (16 bytes per pair and dimension, L2-resident). Same functions, same values, bit for bit.
+// A small persistent grid (a few blocks per SM) on a low-priority stream: it must fill idle slots, not take SMs.
+template <int D>
+__global__ void __launch_bounds__(512) k_draw_normals(const __grid_constant__ DevCtx c, const long long t) {
+    const u64 key = c.sp->key;
+    const long long npairs = (c.N + 1) >> 1;
+    const long long pair0 = c.slot0 >> 1;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    // two pairs per iteration: two independent dependency chains per thread (this kernel runs with ONE warp per
+    // scheduler, so instruction-level parallelism is all the latency hiding it has)
+    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < npairs; p += 2 * stride) {
+        const long long p1 = p + stride;
+        uint64_t w0[2 * D], w1[2 * D];
+        aps_pair_words<D>(key, (u64)(pair0 + p), (u64)t, w0);
+        aps_pair_words<D>(key, (u64)(pair0 + (p1 < npairs ? p1 : p)), (u64)t, w1);
+        double z0[2 * D], z1[2 * D];
+        aps_words_to_normals<D>(w0, z0);
+        aps_words_to_normals<D>(w1, z1);
+        double2 *dst = reinterpret_cast<double2 *>(c.zbuf + p * (2 * D));
+#pragma unroll
+        for (int j = 0; j < D; ++j) dst[j] = make_double2(z0[2 * j], z0[2 * j + 1]);
+        if (p1 < npairs) {
+            double2 *dst1 = reinterpret_cast<double2 *>(c.zbuf + p1 * (2 * D));
+#pragma unroll
+            for (int j = 0; j < D; ++j) dst1[j] = make_double2(z1[2 * j], z1[2 * j + 1]);
+        }
     }
 }
 
@@ -144,7 +181,8 @@ __global__ void APS_K1_BOUNDS k_propagate(const __grid_constant__ DevCtx c, cons
     // the random words do not depend on the ancestors (nor, sharded, on the peers): draw the first pair's
     // before the loads / the wait for the peers
     uint64_t w[2 * D];
-    if (p < npairs) aps_pair_words<D>(key, (u64)(pair0 + p), (u64)t, w);
+    const double *__restrict__ zb = c.zbuf;   // pre-drawn normals of this step (k_draw_normals), or null
+    if (!zb && p < npairs) aps_pair_words<D>(key, (u64)(pair0 + p), (u64)t, w);
     APS_PDL_WAIT();   // everything below reads or writes what the previous kernels of the sweep produce
     if (!MULTI) resolve_fat();
     SpanProbe probe(&c.acc[t], 0, c.dbg & 16);
@@ -195,9 +233,18 @@ __global__ void APS_K1_BOUNDS k_propagate(const __grid_constant__ DevCtx c, cons
                               : *reinterpret_cast<const int2 *>(anc + i0);
         double2 lw2 = make_double2(0.0, 0.0);
         if (!reset) lw2 = *reinterpret_cast<const double2 *>(c.logw + i0);
-        if (p != wp) aps_pair_words<D>(key, (u64)(pair0 + p), (u64)t, w);
         double z[2 * D];
-        if (D > 2) aps_words_to_normals<D>(w, z);   // (d >= 3: registers are the limit -- finish the draw before the gather)
+        if (zb) {
+#pragma unroll
+            for (int j = 0; j < D; ++j) {
+                const double2 v = *reinterpret_cast<const double2 *>(zb + p * (2 * D) + 2 * j);
+                z[2 * j] = v.x;
+                z[2 * j + 1] = v.y;
+            }
+        } else {
+            if (p != wp) aps_pair_words<D>(key, (u64)(pair0 + p), (u64)t, w);
+            if (D > 2) aps_words_to_normals<D>(w, z);   // (d >= 3: registers are the limit -- finish the draw before the gather)
+        }
         double xg[2][D];   // parent states of the two slots
         auto gather = [&](int h) {
             long long a = h ? a2.y : a2.x;  // global parent index
@@ -220,7 +267,7 @@ __global__ void APS_K1_BOUNDS k_propagate(const __grid_constant__ DevCtx c, cons
             gather(0);
             gather(1);
         }
-        if (D <= 2) aps_words_to_normals<D>(w, z);
+        if (D <= 2 && !zb) aps_words_to_normals<D>(w, z);
         double xo[2][D];
         double lwo[2];
 #pragma unroll

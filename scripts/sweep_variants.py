@@ -5,7 +5,7 @@ if len(sys.argv) > 1 and sys.argv[1] == "--child":
     sys.path.insert(0, ROOT)
     from advancedps_b200 import _abi, _lib, models
     import bench
-    h = _lib.Handle(_abi.make_config(models.linear_gaussian(), 10**6, 100))
+    h = _lib.Handle(_abi.make_config(models.linear_gaussian(), int(os.environ.get("APS_SWEEP_N", 10**6)), 100))
     h.set_observations(bench.make_data())
     ms = []
     for k in range(13):
