@@ -665,12 +665,20 @@ static int propagate_grid(aps_handle *h, long long n_local) {
     return (int)g;
 }
 
-static void launch_propagate(aps_handle *h, const DevCtx &c, long long t, Launcher &L) {
+// with_draw: the normals of step t are drawn right here, on the same stream, and count as part of the propagate
+// launch (per-launch profiling and APS_DRAW_SERIAL: no parallel branch)
+static void launch_propagate(aps_handle *h, const DevCtx &c, long long t, Launcher &L, bool with_draw = false) {
     cudaStream_t st = h->stream;
     if (h->grid_prop == 0) h->grid_prop = propagate_grid(h, c.N);
     // slab addressing is resolved here, once per launch (no 64-bit modulo in the kernels)
-    APS_LAUNCH(0, launch_pdl(h->f_prop, h->grid_prop, APS_K1_THREADS, 0, st, h->pdl && t > 1, c, (long long)t, x_slab_of(c, t),
-                             (const double *)x_slab_of(c, t - 1), (const int32_t *)anc_slab_of(c, t - 1)));
+    APS_LAUNCH(0, {
+        if (with_draw) {
+            h->f_draw<<<h->grid_draw, h->threads_draw, 0, st>>>(c, t);
+            ++L.n;
+        }
+        launch_pdl(h->f_prop, h->grid_prop, APS_K1_THREADS, 0, st, h->pdl && t > 1, c, (long long)t, x_slab_of(c, t),
+                   (const double *)x_slab_of(c, t - 1), (const int32_t *)anc_slab_of(c, t - 1));
+    });
 }
 
 static void launch_decision(aps_handle *h, const DevCtx &c, long long t, res_fn f_res, Launcher &L) {
@@ -786,29 +794,25 @@ static long long enqueue_sweep(aps_handle *h, LaunchProf *prof = nullptr) {
         if (draw) cc.zbuf = c.zbuf + (A == 2 ? (u & 1) * h->zbuf_stride : 0);
         return cc;
     };
-    if (draw)
+    if (fork)
         for (long long u = 1; u <= A && u <= c.T; ++u) {
             h->f_draw<<<h->grid_draw, h->threads_draw, 0, st>>>(ctx_for(u), u);
             ++L.n;
         }
     for (long long t = 1; t <= c.T; ++t) {
-        launch_propagate(h, ctx_for(t), t, L);
+        launch_propagate(h, ctx_for(t), t, L, draw && !fork);
         const long long u = t + A;   // the draws that may now overwrite the buffer propagate(t) has read
         auto fork_draws = [&]() {
-            if (fork) {
-                cudaStream_t sd = h->stream_draw[u & 1];
-                cudaEventRecord(h->ev_fork, st);
-                cudaStreamWaitEvent(sd, h->ev_fork, 0);
-                h->f_draw<<<h->grid_draw, h->threads_draw, 0, sd>>>(ctx_for(u), u);
-                cudaEventRecord(h->ev_join[u & 1], sd);
-                ++L.n;
-            } else {
-                APS_LAUNCH(0, h->f_draw<<<h->grid_draw, h->threads_draw, 0, st>>>(ctx_for(u), u));
-            }
+            cudaStream_t sd = h->stream_draw[u & 1];
+            cudaEventRecord(h->ev_fork, st);
+            cudaStreamWaitEvent(sd, h->ev_fork, 0);
+            h->f_draw<<<h->grid_draw, h->threads_draw, 0, sd>>>(ctx_for(u), u);
+            cudaEventRecord(h->ev_join[u & 1], sd);
+            ++L.n;
         };
-        if (draw && u <= c.T && !fork_late) fork_draws();
+        if (fork && u <= c.T && !fork_late) fork_draws();
         APS_LAUNCH(1, launch_pdl(k_normalise<IN_LOGW>, gt, APS_K2_THREADS, 0, st, h->pdl, c, (const double *)c.logw, (long long)t));
-        if (draw && u <= c.T && fork_late) fork_draws();   // beside the resample kernel only (its issue slots are 70 % idle)
+        if (fork && u <= c.T && fork_late) fork_draws();   // beside the resample kernel only (its issue slots are 70 % idle)
         launch_decision(h, c, t, h->f_res, L);
         if (fork && t + 1 <= c.T && t + 1 > A) cudaStreamWaitEvent(st, h->ev_join[(t + 1) & 1], 0);   // the draws of step t + 1
     }

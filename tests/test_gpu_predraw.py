@@ -95,15 +95,22 @@ def test_predrawn_equals_in_kernel_draws(monkeypatch):
 
 @pytest.mark.parametrize("world,N,T,res,thr", [
     (2, 4096, 6, _abi.RESAMPLE_SYSTEMATIC, float("nan")),
+    (2, 8192 * 3, 7, _abi.RESAMPLE_SYSTEMATIC, 0.5),
     (4, 8192 * 3, 7, _abi.RESAMPLE_SYSTEMATIC, 0.5),
     (2, 6400, 5, _abi.RESAMPLE_STRATIFIED, float("nan")),
     (2, 6400, 6, _abi.RESAMPLE_RESIDUAL, float("nan")),
     (8, 8192 * 2, 4, _abi.RESAMPLE_SYSTEMATIC, float("nan")),
 ])
-def test_predrawn_sharded_equals_oracle(world, N, T, res, thr):
+def test_predrawn_sharded_equals_oracle(monkeypatch, world, N, T, res, thr):
     """The sharded sweep with the draws made ahead (ranks emulated on one GPU): every rank draws the normals of
-    its own slot pairs; same result as one GPU and as the oracle."""
+    its own slot pairs; same result as one GPU and as the oracle. More than two EMULATED ranks launch their
+    kernels directly (APS_NO_GRAPH): graphs with parallel branches from four host threads on one GPU do not
+    run concurrently, and ranks that spin on each other then never meet (an artefact of the emulation, see
+    aps_api.cu sweep_impl; one process per GPU replays the graph: tests/test_gpu_multiprocess.py)."""
     from test_gpu_sharded import assert_sharded_equal, run_sharded
+
+    if world > 2:
+        monkeypatch.setenv("APS_NO_GRAPH", "1")
 
     m = models.linear_gaussian()
     _, Y = O.simulate_data(m, T, 0xDA7A0005)
