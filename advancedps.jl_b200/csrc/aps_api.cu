@@ -38,13 +38,14 @@ typedef void (*prop_fn)(const DevCtx, const long long, double *, const double *,
 typedef void (*res_fn)(const DevCtx, const long long, int32_t *, const CUtensorMap);
 typedef void (*pgas_fn)(const DevCtx, const long long, const double *, const int32_t *, int32_t *);
 
-template <int D, int OBS, bool MULTI>
+// PRE: the variant that loads pre-drawn normals (pair kernel, d <= 3; see k_draw_normals)
+template <int D, int OBS, bool MULTI, bool PRE>
 static prop_fn prop_for_dy(int dy) {
     switch (dy) {
-        case 1: return k_propagate<D, 1, OBS, MULTI>;
-        case 2: return k_propagate<D, 2, OBS, MULTI>;
-        case 3: return k_propagate<D, 3, OBS, MULTI>;
-        default: return k_propagate<D, 4, OBS, MULTI>;
+        case 1: return k_propagate<D, 1, OBS, MULTI, PRE>;
+        case 2: return k_propagate<D, 2, OBS, MULTI, PRE>;
+        case 3: return k_propagate<D, 3, OBS, MULTI, PRE>;
+        default: return k_propagate<D, 4, OBS, MULTI, PRE>;
     }
 }
 // d = 4: one thread per slot (k_propagate1); APS_K1_PAIRS=1 selects the pair kernel for comparison
@@ -57,31 +58,32 @@ static prop_fn prop1_for_dy4(int dy) {
         default: return k_propagate1<4, 4, OBS, MULTI>;
     }
 }
-template <int OBS, bool MULTI>
+template <int OBS, bool MULTI, bool PRE>
 static prop_fn prop_for_dim(int d, int dy) {
     switch (d) {
-        case 1: return prop_for_dy<1, OBS, MULTI>(dy);
-        case 2: return prop_for_dy<2, OBS, MULTI>(dy);
-        case 3: return prop_for_dy<3, OBS, MULTI>(dy);
-        default: return getenv("APS_K1_PAIRS") ? prop_for_dy<4, OBS, MULTI>(dy) : prop1_for_dy4<OBS, MULTI>(dy);
+        case 1: return prop_for_dy<1, OBS, MULTI, PRE>(dy);
+        case 2: return prop_for_dy<2, OBS, MULTI, PRE>(dy);
+        case 3: return prop_for_dy<3, OBS, MULTI, PRE>(dy);
+        default: return getenv("APS_K1_PAIRS") ? prop_for_dy<4, OBS, MULTI, false>(dy) : prop1_for_dy4<OBS, MULTI>(dy);
     }
 }
-template <bool MULTI>
+template <bool MULTI, bool PRE>
 static prop_fn pick_propagate_m(int obs, int d, int dy) {
     switch (obs) {
-        case APS_OBS_LINEAR_GAUSS: return prop_for_dim<APS_OBS_LINEAR_GAUSS, MULTI>(d, dy);
-        case APS_OBS_STOCH_VOL: return k_propagate<1, 1, APS_OBS_STOCH_VOL, MULTI>;  // d = dy = 1 (aps_model_prepare)
+        case APS_OBS_LINEAR_GAUSS: return prop_for_dim<APS_OBS_LINEAR_GAUSS, MULTI, PRE>(d, dy);
+        case APS_OBS_STOCH_VOL: return k_propagate<1, 1, APS_OBS_STOCH_VOL, MULTI, PRE>;  // d = dy = 1 (aps_model_prepare)
         default:  // constant log-likelihood: dy is not used
             switch (d) {
-                case 1: return k_propagate<1, 1, APS_OBS_CONST, MULTI>;
-                case 2: return k_propagate<2, 1, APS_OBS_CONST, MULTI>;
-                case 3: return k_propagate<3, 1, APS_OBS_CONST, MULTI>;
+                case 1: return k_propagate<1, 1, APS_OBS_CONST, MULTI, PRE>;
+                case 2: return k_propagate<2, 1, APS_OBS_CONST, MULTI, PRE>;
+                case 3: return k_propagate<3, 1, APS_OBS_CONST, MULTI, PRE>;
                 default: return k_propagate1<4, 1, APS_OBS_CONST, MULTI>;
             }
     }
 }
-static prop_fn pick_propagate(int obs, int d, int dy, bool multi) {
-    return multi ? pick_propagate_m<true>(obs, d, dy) : pick_propagate_m<false>(obs, d, dy);
+static prop_fn pick_propagate(int obs, int d, int dy, bool multi, bool pre = false) {
+    if (pre && d <= 3) return multi ? pick_propagate_m<true, true>(obs, d, dy) : pick_propagate_m<false, true>(obs, d, dy);
+    return multi ? pick_propagate_m<true, false>(obs, d, dy) : pick_propagate_m<false, false>(obs, d, dy);
 }
 static pgas_fn pick_pgas_max(int d) {
     switch (d) {
@@ -278,6 +280,8 @@ struct aps_handle {
     long long pc_t, pc_decided;
     CUtensorMap tmap_q;
     prop_fn f_prop;
+    prop_fn f_prop_pre;   // the variant that loads pre-drawn normals (null: no pre-draw on this handle)
+    int grid_prop_pre;
     res_fn f_res;
     pgas_fn f_pmax, f_psel;
 };
@@ -479,6 +483,8 @@ extern "C" int aps_create(const aps_config *cfg, aps_handle **out) {
                             (getenv("APS_PREDRAW") != nullptr && atoi(getenv("APS_PREDRAW")) != 0);
     if (!h->prop_per_slot && d <= 3 && predraw_ok && getenv("APS_NO_PREDRAW") == nullptr) {
         h->f_draw = d == 1 ? k_draw_normals<1> : d == 2 ? k_draw_normals<2> : k_draw_normals<3>;
+        h->f_prop_pre = pick_propagate(cfg->model.obs_kind, d, cfg->model.dy, world > 1, true);
+        prefer_max_smem(h->f_prop_pre);
         prefer_max_smem(h->f_draw);   // same carve-out as its neighbours: an SM that had to re-partition would serialise them
         const long long npairs = (Nl + 1) / 2;
         h->draw_ahead = 1;
@@ -644,11 +650,11 @@ static int32_t *anc_slab_of(const DevCtx &c, long long sidx) { return c.anc + ((
 // tail) and (b) sized so that every thread runs the SAME number of iterations: with npairs / resident
 // threads = 2.64 (N = 1e6) a maximal grid leaves a third of the blocks idle for the last third of
 // the kernel; ceil(npairs / (iterations x threads)) blocks spread the same work evenly.
-static int propagate_grid(aps_handle *h, long long n_local) {
+static int propagate_grid(aps_handle *h, long long n_local, prop_fn fn) {
     // work items: slot pairs, or slots for the one-thread-per-slot kernel of d = 4
     const long long npairs = h->prop_per_slot ? n_local : (n_local + 1) / 2;
     int occ = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, h->f_prop, APS_K1_THREADS, 0) != cudaSuccess || occ < 1) {
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, APS_K1_THREADS, 0) != cudaSuccess || occ < 1) {
         cudaGetLastError();
         occ = 1;
     }
@@ -669,15 +675,17 @@ static int propagate_grid(aps_handle *h, long long n_local) {
 // launch (per-launch profiling and APS_DRAW_SERIAL: no parallel branch)
 static void launch_propagate(aps_handle *h, const DevCtx &c, long long t, Launcher &L, bool with_draw = false) {
     cudaStream_t st = h->stream;
-    if (h->grid_prop == 0) h->grid_prop = propagate_grid(h, c.N);
+    if (h->grid_prop == 0) h->grid_prop = propagate_grid(h, c.N, h->f_prop);
+    if (h->f_prop_pre && h->grid_prop_pre == 0) h->grid_prop_pre = propagate_grid(h, c.N, h->f_prop_pre);
+    const bool pre = c.zbuf != nullptr && h->f_prop_pre != nullptr;   // the normals of this step were drawn ahead
     // slab addressing is resolved here, once per launch (no 64-bit modulo in the kernels)
     APS_LAUNCH(0, {
         if (with_draw) {
             h->f_draw<<<h->grid_draw, h->threads_draw, 0, st>>>(c, t);
             ++L.n;
         }
-        launch_pdl(h->f_prop, h->grid_prop, APS_K1_THREADS, 0, st, h->pdl && t > 1, c, (long long)t, x_slab_of(c, t),
-                   (const double *)x_slab_of(c, t - 1), (const int32_t *)anc_slab_of(c, t - 1));
+        launch_pdl(pre ? h->f_prop_pre : h->f_prop, pre ? h->grid_prop_pre : h->grid_prop, APS_K1_THREADS, 0, st, h->pdl && t > 1, c,
+                   (long long)t, x_slab_of(c, t), (const double *)x_slab_of(c, t - 1), (const int32_t *)anc_slab_of(c, t - 1));
     });
 }
 
@@ -784,14 +792,16 @@ static long long enqueue_sweep(aps_handle *h, LaunchProf *prof = nullptr) {
     // consumed the buffer they go to -- onto a low-priority stream, run beside the kernels in between, and are
     // joined before propagate(u); A = draw_ahead = 2 gives them more than a whole step (two buffers, two
     // streams: consecutive draw kernels may overlap). Under stream capture these are parallel branches of the
-    // graph. With per-launch profiling everything stays on one stream (class 0, A = 1).
-    const bool draw = c.zbuf != nullptr;
-    const bool fork = draw && prof == nullptr && getenv("APS_DRAW_SERIAL") == nullptr;
+    // graph. Per-launch profiling (aps_sweep_profiled) times the classical step instead -- the propagate kernel
+    // draws its own normals -- so that its per-kernel figures describe whole kernels, not a background kernel
+    // run in the foreground; APS_DRAW_SERIAL=1 keeps the draw kernel but launches it on the sweep's stream.
+    const bool draw = c.zbuf != nullptr && prof == nullptr;
+    const bool fork = draw && getenv("APS_DRAW_SERIAL") == nullptr;
     const int A = fork ? h->draw_ahead : 1;
     const bool fork_late = fork && getenv("APS_DRAW_FORK") != nullptr && atoi(getenv("APS_DRAW_FORK")) == 2;
     auto ctx_for = [&](long long u) {   // the context of step u: its buffer of normals
         DevCtx cc = c;
-        if (draw) cc.zbuf = c.zbuf + (A == 2 ? (u & 1) * h->zbuf_stride : 0);
+        cc.zbuf = draw ? c.zbuf + (A == 2 ? (u & 1) * h->zbuf_stride : 0) : nullptr;
         return cc;
     };
     if (fork)

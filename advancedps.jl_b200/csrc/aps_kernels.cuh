@@ -134,8 +134,14 @@ __global__ void __launch_bounds__(512) k_draw_normals(const __grid_constant__ De
 // Box-Muller normals (aps_pair_normals), ancestors / log-weights / states move as 8- and 16-byte
 // vectors. Block maxima of the new log-weights are folded into one atomicMax per block.
 #define APS_K1_BOUNDS __launch_bounds__(APS_K1_THREADS, APS_K1_MINBLOCKS)
-template <int D, int DY, int OBS, bool MULTI>
-__global__ void APS_K1_BOUNDS k_propagate(const __grid_constant__ DevCtx c, const long long t,
+// PRE: the normals of the step were drawn ahead of time (k_draw_normals) and are loaded from c.zbuf. Without the
+// Philox / Box-Muller state the kernel needs fewer registers, and -- 96 instead of 232 instructions per particle --
+// it is bound by the latency of its loads (ncu: long scoreboard), so it runs with more resident blocks.
+#ifndef APS_K1_MINBLOCKS_PRE
+#define APS_K1_MINBLOCKS_PRE 10   // measured at N = 1e6 (ms per sweep): 8 blocks 2.479, 10 blocks 2.438, 12 blocks (40 registers, spills) 2.470
+#endif
+template <int D, int DY, int OBS, bool MULTI, bool PRE = false>
+__global__ void __launch_bounds__(APS_K1_THREADS, (PRE && D == 1) ? APS_K1_MINBLOCKS_PRE : APS_K1_MINBLOCKS) k_propagate(const __grid_constant__ DevCtx c, const long long t,
                                                            double *__restrict__ xt, const double *__restrict__ xp,
                                                            const int32_t *anc) {  // not __restrict__: patched below
     __shared__ u64 red[APS_K1_THREADS / 32];
@@ -181,8 +187,8 @@ __global__ void APS_K1_BOUNDS k_propagate(const __grid_constant__ DevCtx c, cons
     // the random words do not depend on the ancestors (nor, sharded, on the peers): draw the first pair's
     // before the loads / the wait for the peers
     uint64_t w[2 * D];
-    const double *__restrict__ zb = c.zbuf;   // pre-drawn normals of this step (k_draw_normals), or null
-    if (!zb && p < npairs) aps_pair_words<D>(key, (u64)(pair0 + p), (u64)t, w);
+    const double *__restrict__ zb = PRE ? c.zbuf : nullptr;   // pre-drawn normals of this step (k_draw_normals)
+    if (!PRE && p < npairs) aps_pair_words<D>(key, (u64)(pair0 + p), (u64)t, w);
     APS_PDL_WAIT();   // everything below reads or writes what the previous kernels of the sweep produce
     if (!MULTI) resolve_fat();
     SpanProbe probe(&c.acc[t], 0, c.dbg & 16);
@@ -234,7 +240,7 @@ __global__ void APS_K1_BOUNDS k_propagate(const __grid_constant__ DevCtx c, cons
         double2 lw2 = make_double2(0.0, 0.0);
         if (!reset) lw2 = *reinterpret_cast<const double2 *>(c.logw + i0);
         double z[2 * D];
-        if (zb) {
+        if (PRE) {
 #pragma unroll
             for (int j = 0; j < D; ++j) {
                 const double2 v = *reinterpret_cast<const double2 *>(zb + p * (2 * D) + 2 * j);
@@ -267,7 +273,7 @@ __global__ void APS_K1_BOUNDS k_propagate(const __grid_constant__ DevCtx c, cons
             gather(0);
             gather(1);
         }
-        if (D <= 2 && !zb) aps_words_to_normals<D>(w, z);
+        if (D <= 2 && !PRE) aps_words_to_normals<D>(w, z);
         double xo[2][D];
         double lwo[2];
 #pragma unroll

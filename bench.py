@@ -441,7 +441,12 @@ def main():
                                        "fraction of the in-sweep kernels is a utilisation figure, not their limiter; the HBM-bound "
                                        "measurement is resample_isolated",
                 "whole_step": {"algorithmic_bytes": 40 * N_PARTICLES, "us": step_us, "achieved": step_gbs, "frac": step_gbs / peak},
-                "kernels": kern}
+                "kernels": kern,
+                "kernels_note": "per-launch CUDA events around the kernels of the CLASSICAL step (aps_sweep_profiled: plain launches, the "
+                                "propagate kernel draws its own normals; each figure carries ~5 us of launch head and tail). In the timed "
+                                "graph the draws of step t+1 run ahead on a parallel low-priority branch (k_draw_normals) beside "
+                                "normalise / resample of step t, and the propagate kernel only loads them: whole_step is the figure "
+                                "that describes the product path"}
     # the graded resample kernel in isolation: 2^25 particles (> L2), L2 flushed between launches
     n_iso = 1 << 25
     if rank == 0:
