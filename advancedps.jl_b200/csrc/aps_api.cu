@@ -479,7 +479,10 @@ extern "C" int aps_create(const aps_config *cfg, aps_handle **out) {
     // kernel at this size and the propagate kernel would wait for it -- and large enough that a step is not
     // launch-bound (>= 190 tiles, N >= ~4e5: at 1e5 / 3e5 the extra graph node and its two edges cost 2-3 %; measured gain 3 % at 4e5, 8.5 % at 1e6, 5 % at 1.5e6).
     // APS_PREDRAW=1 forces, APS_NO_PREDRAW=1 disables.
-    const bool predraw_ok = (c.num_tiles >= APS_PREDRAW_MIN_TILES && c.num_tiles <= 740) ||
+    // (systematic / stratified steps only: beside the longer multinomial / residual decision kernels a first
+    //  measurement showed no gain -- 8.32 / 8.88 ms per sweep against 8.26 / 8.63)
+    const bool predraw_ok = (c.num_tiles >= APS_PREDRAW_MIN_TILES && c.num_tiles <= 740 &&
+                             (cfg->resampler == APS_RESAMPLE_SYSTEMATIC || cfg->resampler == APS_RESAMPLE_STRATIFIED)) ||
                             (getenv("APS_PREDRAW") != nullptr && atoi(getenv("APS_PREDRAW")) != 0);
     if (!h->prop_per_slot && d <= 3 && predraw_ok && getenv("APS_NO_PREDRAW") == nullptr) {
         h->f_draw = d == 1 ? k_draw_normals<1> : d == 2 ? k_draw_normals<2> : k_draw_normals<3>;
