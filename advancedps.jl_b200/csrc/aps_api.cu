@@ -49,13 +49,13 @@ static prop_fn prop_for_dy(int dy) {
     }
 }
 // d = 4: one thread per slot (k_propagate1); APS_K1_PAIRS=1 selects the pair kernel for comparison
-template <int OBS, bool MULTI>
+template <int OBS, bool MULTI, bool PRE>
 static prop_fn prop1_for_dy4(int dy) {
     switch (dy) {
-        case 1: return k_propagate1<4, 1, OBS, MULTI>;
-        case 2: return k_propagate1<4, 2, OBS, MULTI>;
-        case 3: return k_propagate1<4, 3, OBS, MULTI>;
-        default: return k_propagate1<4, 4, OBS, MULTI>;
+        case 1: return k_propagate1<4, 1, OBS, MULTI, PRE>;
+        case 2: return k_propagate1<4, 2, OBS, MULTI, PRE>;
+        case 3: return k_propagate1<4, 3, OBS, MULTI, PRE>;
+        default: return k_propagate1<4, 4, OBS, MULTI, PRE>;
     }
 }
 template <int OBS, bool MULTI, bool PRE>
@@ -64,7 +64,7 @@ static prop_fn prop_for_dim(int d, int dy) {
         case 1: return prop_for_dy<1, OBS, MULTI, PRE>(dy);
         case 2: return prop_for_dy<2, OBS, MULTI, PRE>(dy);
         case 3: return prop_for_dy<3, OBS, MULTI, PRE>(dy);
-        default: return getenv("APS_K1_PAIRS") ? prop_for_dy<4, OBS, MULTI, false>(dy) : prop1_for_dy4<OBS, MULTI>(dy);
+        default: return getenv("APS_K1_PAIRS") ? prop_for_dy<4, OBS, MULTI, false>(dy) : prop1_for_dy4<OBS, MULTI, PRE>(dy);
     }
 }
 template <bool MULTI, bool PRE>
@@ -77,12 +77,12 @@ static prop_fn pick_propagate_m(int obs, int d, int dy) {
                 case 1: return k_propagate<1, 1, APS_OBS_CONST, MULTI, PRE>;
                 case 2: return k_propagate<2, 1, APS_OBS_CONST, MULTI, PRE>;
                 case 3: return k_propagate<3, 1, APS_OBS_CONST, MULTI, PRE>;
-                default: return k_propagate1<4, 1, APS_OBS_CONST, MULTI>;
+                default: return k_propagate1<4, 1, APS_OBS_CONST, MULTI, PRE>;
             }
     }
 }
 static prop_fn pick_propagate(int obs, int d, int dy, bool multi, bool pre = false) {
-    if (pre && d <= 3) return multi ? pick_propagate_m<true, true>(obs, d, dy) : pick_propagate_m<false, true>(obs, d, dy);
+    if (pre) return multi ? pick_propagate_m<true, true>(obs, d, dy) : pick_propagate_m<false, true>(obs, d, dy);
     return multi ? pick_propagate_m<true, false>(obs, d, dy) : pick_propagate_m<false, false>(obs, d, dy);
 }
 static pgas_fn pick_pgas_max(int d) {
@@ -484,8 +484,10 @@ extern "C" int aps_create(const aps_config *cfg, aps_handle **out) {
     const bool predraw_ok = (c.num_tiles >= APS_PREDRAW_MIN_TILES && c.num_tiles <= 740 &&
                              (cfg->resampler == APS_RESAMPLE_SYSTEMATIC || cfg->resampler == APS_RESAMPLE_STRATIFIED)) ||
                             (getenv("APS_PREDRAW") != nullptr && atoi(getenv("APS_PREDRAW")) != 0);
-    if (!h->prop_per_slot && d <= 3 && predraw_ok && getenv("APS_NO_PREDRAW") == nullptr) {
-        h->f_draw = d == 1 ? k_draw_normals<1> : d == 2 ? k_draw_normals<2> : k_draw_normals<3>;
+    // d = 4 (k_propagate1, one thread per slot): measured only when forced (APS_PREDRAW=1), see DESIGN section 4
+    const bool predraw_d4 = d == 4 && h->prop_per_slot && getenv("APS_PREDRAW") != nullptr && atoi(getenv("APS_PREDRAW")) != 0;
+    if (((!h->prop_per_slot && d <= 3 && predraw_ok) || predraw_d4) && getenv("APS_NO_PREDRAW") == nullptr) {
+        h->f_draw = d == 1 ? k_draw_normals<1> : d == 2 ? k_draw_normals<2> : d == 3 ? k_draw_normals<3> : k_draw_normals<4>;
         h->f_prop_pre = pick_propagate(cfg->model.obs_kind, d, cfg->model.dy, world > 1, true);
         prefer_max_smem(h->f_prop_pre);
         prefer_max_smem(h->f_draw);   // same carve-out as its neighbours: an SM that had to re-partition would serialise them

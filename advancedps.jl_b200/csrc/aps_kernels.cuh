@@ -365,8 +365,13 @@ __global__ void __launch_bounds__(APS_K1_THREADS, (PRE && D == 1) ? APS_K1_MINBL
 #ifndef APS_K1P_MINBLOCKS
 #define APS_K1P_MINBLOCKS 6
 #endif
-template <int D, int DY, int OBS, bool MULTI>
-__global__ void __launch_bounds__(APS_K1_THREADS, APS_K1P_MINBLOCKS) k_propagate1(const __grid_constant__ DevCtx c, const long long t,
+#ifndef APS_K1P_MINBLOCKS_PRE
+#define APS_K1P_MINBLOCKS_PRE 6
+#endif
+// PRE: the slot's D normals were drawn ahead of time (k_draw_normals<D>: the pair layout [pair][2 D] IS the slot
+// layout [slot][D] -- slot 2p takes the first D normals of its pair, slot 2p+1 the last D)
+template <int D, int DY, int OBS, bool MULTI, bool PRE = false>
+__global__ void __launch_bounds__(APS_K1_THREADS, PRE ? APS_K1P_MINBLOCKS_PRE : APS_K1P_MINBLOCKS) k_propagate1(const __grid_constant__ DevCtx c, const long long t,
                                                                                  double *__restrict__ xt, const double *__restrict__ xp,
                                                                                  const int32_t *anc) {  // not __restrict__: patched below
     static_assert(D % 2 == 0, "one thread per slot needs an even number of Philox blocks per pair");
@@ -406,7 +411,8 @@ __global__ void __launch_bounds__(APS_K1_THREADS, APS_K1P_MINBLOCKS) k_propagate
             aps_philox2x64(g >> 1, aps_ctr1((u64)t, APS_DOM_STATE, (uint32_t)((g & 1) * (D / 2) + j)), key, &w[2 * j], &w[2 * j + 1]);
     };
     uint64_t w[D];
-    if (i < N) draw_words(i, w);
+    const double *__restrict__ zb = PRE ? c.zbuf : nullptr;
+    if (!PRE && i < N) draw_words(i, w);
     if (!MULTI) resolve_fat();
     const bool reset = t == 1 || c.plan[t - 1].resampled != 0;
     if (MULTI) {
@@ -423,10 +429,19 @@ __global__ void __launch_bounds__(APS_K1_THREADS, APS_K1P_MINBLOCKS) k_propagate
         if (t > 1) a = MULTI ? __ldcg(anc + i) : anc[i];
         double lw_old = 0.0;
         if (!reset) lw_old = c.logw[i];
-        if (!first) draw_words(i, w);
         double z[D];
+        if (PRE) {
 #pragma unroll
-        for (int j = 0; j < D / 2; ++j) aps_normal_pair(w[2 * j], w[2 * j + 1], &z[2 * j], &z[2 * j + 1]);
+            for (int j = 0; j < D / 2; ++j) {
+                const double2 v = *reinterpret_cast<const double2 *>(zb + i * D + 2 * j);
+                z[2 * j] = v.x;
+                z[2 * j + 1] = v.y;
+            }
+        } else {
+            if (!first) draw_words(i, w);
+#pragma unroll
+            for (int j = 0; j < D / 2; ++j) aps_normal_pair(w[2 * j], w[2 * j + 1], &z[2 * j], &z[2 * j + 1]);
+        }
         double x[D];
         if (has_ref && c.slot0 + i == c.Ng - 1) {  // the reference keeps the globally last slot
 #pragma unroll

@@ -60,6 +60,15 @@ def test_predrawn_d2_d3(d):
     assert_sweep_equal(cfg, ro, h, le)
 
 
+def test_predrawn_d4_per_slot_kernel():
+    """d = 4 runs k_propagate1 (one thread per slot); its PRE variant reads the slot's four normals from the same
+    pair-layout buffer. Opt-in only (APS_PREDRAW=1): at the configs[2] shape it is slower than drawing in the
+    kernel, but the path must stay correct."""
+    cfg, Y, ro, h, le = both(models.lg4(), 20001, 9, 7)
+    assert h.last_sweep_launches() == 4 * 9 + 2
+    assert_sweep_equal(cfg, ro, h, le)
+
+
 def test_predrawn_sv_pgas_conditional():
     """Conditional PGAS sweeps (reference trajectory in the last slot) on the three-kernel path."""
     m = models.stochastic_volatility()
