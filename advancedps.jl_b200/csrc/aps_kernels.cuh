@@ -50,7 +50,7 @@ struct DevCtx {
     long long slot0;       // global index of this rank's first slot
     const PeerTable *peers; // device copy of the peer table, or null on one GPU
     int rank, world;
-    int dbg, defer_plan;   // defer_plan: one GPU, few tiles: k_resample derives totals / prefix / plan itself (k_normalise has no last-block phase); dbg: diagnostics only (APS_DEBUG_MULTI): 1 skip waits, 2 skip sys fences, 4 local gathers, 8 local scatter
+    int dbg, defer_plan;   // defer_plan: one GPU, few tiles: k_resample derives totals / prefix / plan itself (k_normalise has no last-block phase); dbg: diagnostics only (APS_DEBUG_MULTI): 1 skip waits, 2 no early iterations in the sharded propagate kernel, 4 local gathers, 8 local scatter, 16 in-graph timeline, 32 per-phase times of the fused kernel, 64 maximum posted by the propagate kernel's last block (round-1 scheme), 512 early PDL trigger
     int *fat_cnt;          // [steps] entries in the fat-parent list of each decision point
     FatEntry *fat;         // [steps][APS_FAT_MAX]
     long long fat_steps;   // steps the lists are sized for (T + 2; 1 at the operator level)
