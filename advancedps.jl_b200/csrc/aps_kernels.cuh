@@ -135,7 +135,7 @@ __global__ void __launch_bounds__(512) k_draw_normals(const __grid_constant__ De
 // vectors. Block maxima of the new log-weights are folded into one atomicMax per block.
 #define APS_K1_BOUNDS __launch_bounds__(APS_K1_THREADS, APS_K1_MINBLOCKS)
 // PRE: the normals of the step were drawn ahead of time (k_draw_normals) and are loaded from c.zbuf. Without the
-// Philox / Box-Muller state the kernel needs fewer registers, and -- 96 instead of 232 instructions per particle --
+// Philox / Box-Muller state the kernel needs fewer registers, and -- 92 instead of 232 instructions per particle --
 // it is bound by the latency of its loads (ncu: long scoreboard), so it runs with more resident blocks.
 #ifndef APS_K1_MINBLOCKS_PRE
 #define APS_K1_MINBLOCKS_PRE 10   // measured at N = 1e6 (ms per sweep): 8 blocks 2.479, 10 blocks 2.438, 12 blocks (40 registers, spills) 2.470

@@ -1,5 +1,5 @@
 """Short targets for ncu: one C2 sweep launched kernel by kernel, the fused persistent sweep kernel,
-the isolated resample kernel at N = 2^25.   usage: profile_target.py {both|sweep|resample|fused|pgas}"""
+the isolated resample kernel at N = 2^25.   usage: profile_target.py {both|sweep|predraw|resample|fused|pgas}"""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -18,6 +18,12 @@ if mode in ("both", "sweep"):
     h.sweep_profiled(1)   # plain launches (no graph) so ncu sees every kernel
     le, ms, n = h.sweep_profiled(2)
     print("sweep", le, ms, n)
+if mode == "predraw":     # the product path of C2, launched directly (APS_NO_GRAPH) so ncu sees k_draw_normals and k_propagate<..., PRE>
+    os.environ["APS_NO_GRAPH"] = "1"
+    cfg = _abi.make_config(models.linear_gaussian(), 1_000_000, T)
+    h = _lib.Handle(cfg)
+    h.set_observations(bench.make_data()[:T])
+    print("predraw", h.sweep(1), h.sweep(2), h.last_sweep_launches(), h.last_sweep_ms())
 if mode == "fused":       # the whole sweep as ONE cooperative launch (csrc/aps_fused.cuh)
     cfg = _abi.make_config(models.linear_gaussian(), 1_000_000, T)
     h = _lib.Handle(cfg)
